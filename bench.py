@@ -1,0 +1,367 @@
+#!/usr/bin/env python
+"""Pool-scoring benchmark (BASELINE.json metric: pool pixels scored / s, + HBM roofline).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--workload cfg2] [--impl reference]
+
+One "step" = one pass of the hot path over the whole synthetic pool of the workload:
+als_pool_begin -> als_pool_score_batch per chunk -> als_pool_select (+ NCCL all-gather of the
+per-GPU candidates when N > 1).  Default workload = BASELINE.json configs[1] (ENet MC-dropout T=8
+variance, 2975 images @512x1024, C=19, fp32).  Multi-GPU is weak scaling: every rank scores its
+own 2975-image shard of an N x 2975 pool; the only exchange is the candidate/score all-gather.
+
+The pool does not fit HBM (948 GB of logits per shard), so storage is aliased: `resident`
+distinct images live in HBM and pool image n reads slot n % resident.  Every byte scored comes
+from HBM (the resident set is hundreds of times the 126 MB L2).
+
+Prints ONE JSON line (see README / DESIGN.md section "Measurement").
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+WORKLOADS = {
+    # name: per-GPU pool N, T, H, W, C, measure, resident images, chunk images, description
+    "cfg1": dict(N=64, T=1, H=512, W=1024, C=19, measure="entropy", resident=64, chunk=64,
+                 desc="ENet Cityscapes 19-class entropy, pool 64 @512x1024"),
+    "cfg2": dict(N=2975, T=8, H=512, W=1024, C=19, measure="variance", resident=175, chunk=175,
+                 desc="ENet MC-dropout T=8 variance, pool 2975 @512x1024, C=19"),
+    "cfg3": dict(N=372, T=1, H=1024, W=2048, C=19, measure="margin", resident=372, chunk=124,
+                 desc="full-res 1024x2048 margin, 2975-image pool sharded 8 ways (372 per GPU)"),
+    "cfg4": dict(N=4096, T=1, H=480, W=640, C=6, measure="entropy", resident=4096, chunk=512,
+                 desc="Freiburg Forest 6-class entropy @480x640, pool 4096"),
+    "cfg5": dict(N=2250, T=16, H=512, W=1024, C=66, measure="variance", resident=50, chunk=50,
+                 desc="Mapillary Vistas 66-class MC-dropout T=16, 18000-image pool sharded 8 ways (2250 per GPU)"),
+}
+K_SELECT = 50          # conf/enet_cityscapes_active_learning.json:59
+SEED = 20191013
+
+
+def parse_args():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--workload", default="cfg2", choices=sorted(WORKLOADS))
+    ap.add_argument("--dtype", default="f32", choices=["f32", "bf16"])
+    ap.add_argument("--pool", type=int, default=0, help="override the per-GPU pool size")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--cpu-seconds", type=float, default=12.0, help="budget for the CPU baseline sample")
+    return ap.parse_args()
+
+
+def load_peaks():
+    try:
+        with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
+            return float(json.load(f)["hbm_gbs"]), "measured (MEASURED_PEAKS.json)"
+    except Exception:
+        return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+# ------------------------------------------------------------------------------------------------
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled DURING the timed region."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index: int):
+        self.idx = gpu_index
+        self.rows = []
+        self.proc = None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "--query-gpu=" + self.Q, "--format=csv,noheader,nounits",
+                                          "-lms", "100", "-i", str(self.idx)], stdout=subprocess.PIPE,
+                                         stderr=subprocess.DEVNULL, text=True)
+            self.thread = threading.Thread(target=self._read, daemon=True)
+            self.thread.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append(line.strip())
+
+    def stop(self) -> dict:
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons, power = [], [], set(), []
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for r in self.rows:
+            f = [c.strip() for c in r.split(",")]
+            if len(f) < 8:
+                continue
+            try:
+                sm.append(float(f[1])); mx.append(float(f[2])); power.append(float(f[3]))
+            except ValueError:
+                continue
+            for nm, v in zip(names, f[4:8]):
+                if v.lower().startswith("active"):
+                    reasons.add(nm)
+        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "power_w_max": max(power) if power else None, "samples": len(sm), "reasons": sorted(reasons)}
+
+
+# ------------------------------------------------------------------------------------------------
+def cpu_reference_rate(w, seconds: float, dtype: str):
+    """The CPU restatement of the reference graph (oracle/reference_torch.py, all host threads) on a
+    bounded sample of the same workload.  Returns (pixels/s, cores, sample description, ids check)."""
+    import torch
+    from oracle import reference_torch as RT, synth
+    cores = RT.set_threads()
+    T, H, W, C = w["T"], w["H"], w["W"], w["C"]
+    n_img = 2
+    x = torch.from_numpy(synth.synth_logits(T, 0, n_img, H, W, C, seed=SEED, squeeze_t=False))
+    if T == 1:
+        x = x[0]
+    RT.score_pool(x[:1] if T == 1 else x[:, :1], w["measure"])          # warm-up
+    t0 = time.perf_counter()
+    done = 0
+    while True:
+        RT.score_pool(x, w["measure"])
+        done += n_img
+        el = time.perf_counter() - t0
+        if el >= seconds or done >= 64:
+            break
+    rate = done * H * W / el
+    return rate, cores, "%d images x T=%d @%dx%dx%d, %s, torch CPU op-by-op, %.1f s" % (done, T, H, W, C, w["measure"], el)
+
+
+def run_reference(args):
+    """--impl reference: the reference's CPU implementation of the path (restated op by op; TF 1.13 is
+    not installable), all host threads, bounded sample per step.  Rank 0 only."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    import torch
+    from oracle import reference_torch as RT, synth
+    w = dict(WORKLOADS[args.workload])
+    cores = RT.set_threads()
+    T, H, W, C = w["T"], w["H"], w["W"], w["C"]
+    n_img = 2                                   # images per step (bounded sample of the pool)
+    x = torch.from_numpy(synth.synth_logits(T, 0, n_img, H, W, C, seed=SEED, squeeze_t=False))
+    if T == 1:
+        x = x[0]
+    unl = np.arange(n_img)
+    for _ in range(max(args.warmup, 1)):
+        RT.rank_confidence(x, unl, 1, w["measure"], batch_size=8)
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        RT.rank_confidence(x, unl, 1, w["measure"], batch_size=8)
+    el = time.perf_counter() - t0
+    rate = args.steps * n_img * H * W / el / 1e9
+    sample = "%d images x T=%d @%dx%dx%d per step (bounded sample of the %d-image pool), %s" % (
+        n_img, T, H, W, C, w["N"], w["measure"])
+    line = {
+        "impl": "reference", "metric": "pool pixels scored/s", "value": rate, "unit": "Gpix/s",
+        "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": el / args.steps * 1e3,
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": args.workload + ": " + w["desc"], "k": K_SELECT, "sample": sample},
+        "cpu_baseline": {"value": rate, "unit": "Gpix/s", "cores": cores, "kind": "port", "sample": sample},
+        "e2e": {"value": rate, "unit": "Gpix/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+        "note": "TensorFlow 1.13.2 cannot be installed here; this is the op-by-op torch-CPU restatement of "
+                "active_learning.py:239-263,682-715 (oracle/reference_torch.py) on all host threads",
+    }
+    print(json.dumps(line), flush=True)
+
+
+# ------------------------------------------------------------------------------------------------
+def main():
+    args = parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+        return
+
+    import torch
+    import torch.distributed as dist
+    from semanticsegmentationactivelearning_b200 import Scorer, rank_confidence_sharded
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a GPU (the pool-scoring path has no CPU fallback)")
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=dev)
+
+    w = dict(WORKLOADS[args.workload])
+    if args.pool:
+        w["N"] = args.pool
+    T, H, W, C, N = w["T"], w["H"], w["W"], w["C"], w["N"]
+    measure = w["measure"]
+    dtype = "float32" if args.dtype == "f32" else "bfloat16"
+    es = 4 if args.dtype == "f32" else 2
+    resident = min(w["resident"], N)
+    chunk = min(w["chunk"], resident)
+    P = H * W
+    id0 = rank * N                                    # this rank's global example ids: [id0, id0 + N)
+
+    sc = Scorer(local_rank)
+    # resident logits [T, resident, H, W, C]; chunks are dense [T, chunk, ...] tensors of their own
+    n_chunk_bufs = resident // chunk
+    bufs = [sc.synth_logits(T, id0 + i * chunk, chunk, H, W, C, dtype=dtype, seed=SEED, squeeze_t=False)
+            for i in range(n_chunk_bufs)]
+    torch.cuda.synchronize()
+    # pool chunk list: (buffer, first local id, count)
+    chunks = []
+    n0 = 0
+    while n0 < N:
+        nb = min(chunk, N - n0)
+        buf = bufs[(n0 // chunk) % n_chunk_bufs]
+        if nb < chunk:   # ragged tail: a dense [T, nb] tensor of its own
+            buf = sc.synth_logits(T, id0 + n0, nb, H, W, C, dtype=dtype, seed=SEED, squeeze_t=False)
+        chunks.append((buf, n0, nb))
+        n0 += nb
+    unl_local = np.arange(N, dtype=np.int64)          # every pool image is unlabelled
+    unl_global = np.arange(world * N, dtype=np.int64)
+
+    ev_pairs = []
+
+    def step(record: bool):
+        sc.pool_begin(N)
+        for buf, first, nb in chunks:
+            idx = np.arange(first, first + nb, dtype=np.int64)
+            if record:
+                e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                e0.record()
+            sc.pool_score_batch(buf, idx, measure)
+            if record:
+                e1.record()
+                ev_pairs.append((e0, e1, nb))
+        if world == 1:
+            ids, conf = sc.pool_select(unl_local, K_SELECT)
+        else:
+            scores = sc.pool_scores(N)
+            ids, conf = rank_confidence_sharded(scores, id0 + unl_local, unl_global, K_SELECT, scorer=sc)
+        return ids, conf
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for _ in range(max(args.warmup, 3)):
+        step(False)
+    barrier()
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+    launches0 = sc.launch_count
+    t_start, t_end = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    t_start.record()
+    for _ in range(args.steps):
+        ids, conf = step(True)
+    t_end.record()
+    barrier()
+    ms_total = t_start.elapsed_time(t_end)
+    launches = sc.launch_count - launches0
+    clocks = sampler.stop() if rank == 0 else None
+    if world > 1:
+        t = torch.tensor([ms_total], device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms_total = float(t.item())
+    ms_step = ms_total / args.steps
+    value = world * N * P / (ms_step * 1e-3) / 1e9
+
+    # dominant kernel: score_tiles_kernel, one launch per chunk (the 2 us finalize launch rides along)
+    full = [(a.elapsed_time(b), nb) for a, b, nb in ev_pairs if nb == chunk] or [(a.elapsed_time(b), nb) for a, b, nb in ev_pairs]
+    avg_ms = sum(m for m, _ in full) / len(full)
+    bytes_launch = full[0][1] * T * P * C * es
+    peak, peak_src = load_peaks()
+    achieved = bytes_launch / (avg_ms * 1e-3) / 1e9
+    kernel_share = sum(a.elapsed_time(b) for a, b, _ in ev_pairs) / ms_total
+
+    # ---- e2e: the public API with HOST (pinned) logits, H2D inside the timed region ----------------
+    e2e = None
+    if not args.no_e2e:
+        from semanticsegmentationactivelearning_b200 import rank_confidence
+        per_img = T * P * C * es
+        bsz = max(1, min(8, int((2 << 30) // per_img)))              # images per sess.run-like batch (<= 8, :689)
+        n_e2e = max(bsz, min(N, int((8 << 30) // per_img) // bsz * bsz))   # ~8 GB of logits per step
+        tdt = torch.float32 if args.dtype == "f32" else torch.bfloat16
+        host = torch.empty((T, bsz, H, W, C), dtype=tdt).pin_memory()
+        host.copy_(bufs[0][:, :bsz])
+        torch.cuda.synchronize()
+        host_np_batches = None
+
+        def e2e_step():
+            batches = ((host if T > 1 else host[0], np.arange(i, i + bsz, dtype=np.int64)) for i in range(0, n_e2e, bsz))
+            return rank_confidence(batches, np.arange(n_e2e, dtype=np.int64), K_SELECT, measure, num_examples=n_e2e,
+                                   scorer=sc)
+
+        e2e_step()
+        barrier()
+        t0 = time.perf_counter()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        k_e2e = max(2, min(args.steps, 5))
+        for _ in range(k_e2e):
+            ids_e, conf_e = e2e_step()
+        e1.record()
+        barrier()
+        ms_e = e0.elapsed_time(e1) / k_e2e
+        if world > 1:
+            t = torch.tensor([ms_e], device=dev)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            ms_e = float(t.item())
+        e2e = {"value": world * n_e2e * P / (ms_e * 1e-3) / 1e9, "unit": "Gpix/s",
+               "h2d_bytes_per_step": int(n_e2e * per_img + n_e2e * 8 + n_e2e * 8),
+               "d2h_bytes_per_step": int(min(K_SELECT, n_e2e) * 8 + n_e2e * 4),
+               "pool_images_per_step": n_e2e, "batch_images": bsz, "ms_per_step": ms_e,
+               "note": "rank_confidence() fed pinned host batches like sess.run (:697-700); PCIe-bound"}
+
+    if rank == 0:
+        cpu = None
+        if not args.no_cpu_baseline and world == 1:
+            rate, cores, sample = cpu_reference_rate(w, args.cpu_seconds, dtype)
+            cpu = {"value": rate / 1e9, "unit": "Gpix/s", "cores": cores, "kind": "port", "sample": sample}
+        desc = sc.describe_launch(dtype, T, chunk, H, W, C, measure)
+        line = {
+            "metric": "pool pixels scored/s", "value": value, "unit": "Gpix/s", "n_gpus": world,
+            "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": ms_step, "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": args.dtype, "data": "synthetic",
+            "config": {"workload": args.workload + ": " + w["desc"], "pool_images_per_gpu": N, "T": T, "H": H, "W": W,
+                       "C": C, "measure": measure, "k": K_SELECT, "resident_images": resident, "chunk_images": chunk,
+                       "l2": "inputs larger than L2 (resident set %.1f GB, aliased over the pool)" % (resident * T * P * C * es / 1e9),
+                       "kernel": desc},
+            "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches * world),
+            "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                         "traffic": None, "peak_source": peak_src, "kernel": desc["kernel"],
+                         "bytes_per_launch": bytes_launch, "avg_launch_ms": avg_ms, "launches_timed": len(full),
+                         "kernel_share_of_step": kernel_share},
+            "cpu_baseline": cpu,
+            "selected_ids_head": [int(i) for i in ids[:5]],
+        }
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

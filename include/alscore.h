@@ -1,0 +1,189 @@
+/*
+ * alscore.h -- C ABI of the B200-native pool-scoring path.
+ *
+ * Drop-in boundary for the acquisition step of
+ * alfrunesiq/SemanticSegmentationActiveLearning.  The reference has no FFI of its
+ * own (it is TensorFlow graph code inline in main()), so every entry point cites
+ * the reference lines (relative to /root/reference) whose behaviour it replaces.
+ * INTEGRATION.md shows the ctypes binding a maintainer adds on the reference side.
+ *
+ * Conventions
+ *   - plain pointers and sizes only; no framework types.
+ *   - logits are dense NHWC, class innermost:  [N,H,W,C]  or  [T,N,H,W,C]
+ *     (T Monte-Carlo samples outermost), float32 or bfloat16, 16-byte aligned.
+ *     (reference: pseudo_logits, active_learning.py:231; models/enet/enet_modules.py:1376-1380)
+ *   - "device" pointers must belong to the context's GPU; "host" pointers are
+ *     staged to the GPU (never scored on the CPU -- there is no CPU fallback).
+ *   - every function returns ALS_OK (0) or a negative als_status; the message is
+ *     available from als_last_error().  Outputs are never partially filled on error.
+ *   - calls are synchronous with respect to the host unless a function says otherwise;
+ *     `stream` is a cudaStream_t (NULL = the context's own stream).
+ */
+#ifndef ALSCORE_H_
+#define ALSCORE_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define ALS_VERSION 100 /* 0.1.0 */
+
+#if defined(__GNUC__)
+#define ALS_API __attribute__((visibility("default")))
+#else
+#define ALS_API
+#endif
+
+typedef struct als_ctx als_ctx;
+
+typedef enum als_status {
+  ALS_OK = 0,
+  ALS_ERR_INVALID = -1,     /* bad shape / dtype / stride / alignment / NULL pointer   -> ValueError        */
+  ALS_ERR_UNSUPPORTED = -2, /* unknown measure (active_learning.py:259-260)            -> NotImplementedError */
+  ALS_ERR_CUDA = -3,        /* CUDA runtime error                                       -> RuntimeError      */
+  ALS_ERR_NOMEM = -4,       /* allocation failed                                        -> MemoryError       */
+  ALS_ERR_STATE = -5        /* call sequence error (e.g. pool not begun)                -> RuntimeError      */
+} als_status;
+
+/* alparams["measure"] (active_learning.py:240,252,256; conf/default_params.json:49).
+ * ALS_VARIANCE is an extension (MC-dropout; needs T >= 2), absent from the reference. */
+typedef enum als_measure {
+  ALS_ENTROPY = 0,    /* 1 - H(p)/log(C)            active_learning.py:240-251 */
+  ALS_MARGIN = 1,     /* p(1) - p(2)                active_learning.py:252-255 */
+  ALS_CONFIDENCE = 2, /* max_c p                    active_learning.py:256-258 */
+  ALS_VARIANCE = 3    /* 1 - sum_c Var_t[p_t,c]     (extension)               */
+} als_measure;
+
+typedef enum als_dtype { ALS_F32 = 0, ALS_BF16 = 1 } als_dtype;
+
+/* ---- library / context ------------------------------------------------------------ */
+
+ALS_API int als_version(void);
+
+/* Number of CUDA devices visible, or a negative als_status. */
+ALS_API int als_device_count(void);
+
+/* One context per GPU and per host thread: owns a stream, scratch accumulators,
+ * staging buffers and the pool score vector. */
+ALS_API int als_ctx_create(int device, als_ctx** out);
+ALS_API int als_ctx_destroy(als_ctx* ctx);
+
+/* Make all of the context's work run on the caller's cudaStream_t (e.g. the framework's current
+ * stream, so scoring is ordered after the kernels that produced the logits).  The context does
+ * not take ownership.  NULL is the legacy default stream. */
+ALS_API int als_ctx_set_stream(als_ctx* ctx, void* stream);
+
+/* Last error message of this context (ctx == NULL: of the calling thread). */
+ALS_API const char* als_last_error(const als_ctx* ctx);
+
+/* "entropy" | "margin" | "confidence" | "variance" -> als_measure.
+ * Unknown names return ALS_ERR_UNSUPPORTED with the reference's message
+ * "Uncertainty function not implemented." (active_learning.py:259-260). */
+ALS_API int als_measure_from_name(const char* name, int* measure);
+
+/* Count of this library's kernel launches issued through ctx since creation. */
+ALS_API int64_t als_launch_count(const als_ctx* ctx);
+
+/* ---- graph-level boundary (replaces active_learning.py:234-269) ------------------- */
+
+/*
+ * Score N images held in DEVICE memory.
+ *   logits     device, [T,N,H,W,C] (T == 1: [N,H,W,C]), dtype f32/bf16, 16-byte aligned
+ *   scores     device f64[N]     pseudo_mean_confidence (active_learning.py:261-263); required
+ * Optional per-pixel outputs (device, may each be NULL) -- the training-path consumers:
+ *   conf_map   f32[N,H,W]        pseudo_confidence      (active_learning.py:251/255/258)
+ *   label      u8[N,H,W]         pseudo_label           (active_learning.py:234-236; sample 0 if T > 1)
+ *   mask       u8[N,H,W]         pseudo_mask            (active_learning.py:265-269), conf < threshold ? 0 : 1
+ * Asynchronous on `stream`; the caller synchronises.
+ */
+ALS_API int als_score(als_ctx* ctx, const void* logits, int dtype,
+              int64_t T, int64_t N, int64_t H, int64_t W, int64_t C, int measure,
+              double* scores, float* conf_map, uint8_t* label, uint8_t* mask, float threshold,
+              void* stream);
+
+/*
+ * Same for logits in HOST memory (pinned or pageable): staged host->device in chunks on a
+ * copy stream, overlapped with scoring; `scores` is host f64[N]; per-pixel outputs (host,
+ * optional) are copied back.  Synchronous.
+ */
+ALS_API int als_score_host(als_ctx* ctx, const void* logits, int dtype,
+                   int64_t T, int64_t N, int64_t H, int64_t W, int64_t C, int measure,
+                   double* scores, float* conf_map, uint8_t* label, uint8_t* mask, float threshold);
+
+/*
+ * DLPack entry: `managed` is a DLManagedTensor* (dlpack.h, v0.x ABI) taken from a
+ * "dltensor" capsule.  kDLCUDA / kDLCUDAManaged tensors are scored in place (zero copy),
+ * kDLCPU / kDLCUDAHost are staged.  Checks dtype in {f32, bf16}, ndim in {4,5}, dense
+ * C-order strides, 16-byte alignment; anything else is ALS_ERR_INVALID (never a silent copy).
+ * `scores` is HOST f64[N].  The tensor is only borrowed; the caller keeps ownership and
+ * runs the deleter.  Synchronous.
+ */
+ALS_API int als_score_dlpack(als_ctx* ctx, void* managed, int measure, double* scores);
+
+/* ---- loop-level boundary (replaces rank_confidence, active_learning.py:682-715) ---- */
+
+/* :684-685  confidence = np.zeros(num_examples, float32)  (device-resident). */
+ALS_API int als_pool_begin(als_ctx* ctx, int64_t num_examples);
+
+/*
+ * :697-700  one sess.run + scatter:  confidence[example_index[b]] = float32(score64[b]).
+ *   logits         [T,B,H,W,C] in device (logits_on_host == 0) or host memory
+ *   example_index  HOST int64[B], each in [0, num_examples)
+ * Asynchronous w.r.t. the host for device logits; host logits return once staged.
+ */
+ALS_API int als_pool_score_batch(als_ctx* ctx, const void* logits, int logits_on_host, int dtype,
+                         int64_t T, int64_t B, int64_t H, int64_t W, int64_t C, int measure,
+                         const int64_t* example_index);
+
+/* Copy the whole f32[num_examples] confidence vector to the host (synchronises). */
+ALS_API int als_pool_scores(als_ctx* ctx, float* out, int64_t num_examples);
+
+/*
+ * :705-715  filter to `unlabelled`, pick the k = min(M, selection_size) LOWEST confidences.
+ *   unlabelled              HOST int64[M], unique ids in [0, num_examples)
+ *   out_ids                 HOST int64[min(k, M)], ascending in (confidence, id)
+ *   out_unlabelled_conf     HOST f32[M]  == confidence[unlabelled]           (may be NULL)
+ *   out_count               number of ids written
+ * Total order (the reference leaves these to np.argpartition's whim): -0.0 == +0.0,
+ * NaN after +inf, ties broken by the lower example id; k >= M returns all M
+ * (the reference raises ValueError there).  Synchronous.
+ */
+ALS_API int als_pool_select(als_ctx* ctx, const int64_t* unlabelled, int64_t M, int64_t selection_size,
+                    int64_t* out_ids, float* out_unlabelled_conf, int64_t* out_count);
+
+/*
+ * Device-level selection primitive (block-radix select), also used to merge the
+ * per-GPU candidates after the all-gather.
+ *   keys  device f32[M];  ids  device int64[M] (unique);  k >= 0
+ *   out_keys device f32[min(k,M)], out_ids device int64[min(k,M)], ascending in (key, id).
+ * Asynchronous on `stream`.
+ */
+ALS_API int als_select_smallest(als_ctx* ctx, const float* keys, const int64_t* ids, int64_t M, int64_t k,
+                        float* out_keys, int64_t* out_ids, void* stream);
+
+/* ---- synthetic pool (bench / tests) ------------------------------------------------ */
+
+/*
+ * Counter-based logits generator, bit-identical to oracle/synth.py.  Writes images
+ * n0 .. n0+n_imgs-1 of the synthetic pool as device [T, n_imgs, H, W, C].
+ * mc != 0 adds the per-sample noise term (use mc = (T > 1)).  Asynchronous on `stream`.
+ */
+ALS_API int als_synth_logits(als_ctx* ctx, void* out, int dtype, int64_t T, int64_t n0, int64_t n_imgs,
+                     int64_t H, int64_t W, int64_t C, uint64_t seed, int mc, void* stream);
+
+/* Write `bytes` of device scratch (> L2) so the next timed launch starts cold. */
+ALS_API int als_flush_l2(als_ctx* ctx, void* stream);
+
+/* Describe the kernel als_score would launch for this shape (for bench / profiles):
+ * fills name (<= 127 chars), grid, block, dynamic smem bytes, pipeline stages, pixels per tile. */
+ALS_API int als_describe_launch(als_ctx* ctx, int dtype, int64_t T, int64_t N, int64_t H, int64_t W, int64_t C,
+                        int measure, char* name, int* grid, int* block, int* smem_bytes, int* stages,
+                        int* tile_pixels);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* ALSCORE_H_ */

@@ -1,0 +1,92 @@
+"""ctypes binding of libalscore.so (include/alscore.h).  No fallback: if the CUDA library is
+missing or there is no B200, every entry point raises."""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+PKG = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(PKG, "libalscore.so")
+
+ALS_OK = 0
+ALS_ERR_INVALID = -1
+ALS_ERR_UNSUPPORTED = -2
+ALS_ERR_CUDA = -3
+ALS_ERR_NOMEM = -4
+ALS_ERR_STATE = -5
+
+ALS_F32, ALS_BF16 = 0, 1
+ALS_ENTROPY, ALS_MARGIN, ALS_CONFIDENCE, ALS_VARIANCE = 0, 1, 2, 3
+
+_i64 = C.c_int64
+_p = C.c_void_p
+
+# name -> (restype, argtypes); must list every symbol include/alscore.h declares
+SIGNATURES = {
+    "als_version": (C.c_int, []),
+    "als_device_count": (C.c_int, []),
+    "als_ctx_create": (C.c_int, [C.c_int, C.POINTER(_p)]),
+    "als_ctx_destroy": (C.c_int, [_p]),
+    "als_ctx_set_stream": (C.c_int, [_p, _p]),
+    "als_last_error": (C.c_char_p, [_p]),
+    "als_measure_from_name": (C.c_int, [C.c_char_p, C.POINTER(C.c_int)]),
+    "als_launch_count": (_i64, [_p]),
+    "als_score": (C.c_int, [_p, _p, C.c_int, _i64, _i64, _i64, _i64, _i64, C.c_int, _p, _p, _p, _p, C.c_float, _p]),
+    "als_score_host": (C.c_int, [_p, _p, C.c_int, _i64, _i64, _i64, _i64, _i64, C.c_int, _p, _p, _p, _p, C.c_float]),
+    "als_score_dlpack": (C.c_int, [_p, _p, C.c_int, _p]),
+    "als_pool_begin": (C.c_int, [_p, _i64]),
+    "als_pool_score_batch": (C.c_int, [_p, _p, C.c_int, C.c_int, _i64, _i64, _i64, _i64, _i64, C.c_int, _p]),
+    "als_pool_scores": (C.c_int, [_p, _p, _i64]),
+    "als_pool_select": (C.c_int, [_p, _p, _i64, _i64, _p, _p, C.POINTER(_i64)]),
+    "als_select_smallest": (C.c_int, [_p, _p, _p, _i64, _i64, _p, _p, _p]),
+    "als_synth_logits": (C.c_int, [_p, _p, C.c_int, _i64, _i64, _i64, _i64, _i64, _i64, C.c_uint64, C.c_int, _p]),
+    "als_flush_l2": (C.c_int, [_p, _p]),
+    "als_describe_launch": (C.c_int, [_p, C.c_int, _i64, _i64, _i64, _i64, _i64, C.c_int, C.c_char_p,
+                                      C.POINTER(C.c_int), C.POINTER(C.c_int), C.POINTER(C.c_int),
+                                      C.POINTER(C.c_int), C.POINTER(C.c_int)]),
+}
+
+_lib = None
+
+
+class AlscoreUnavailable(RuntimeError):
+    """The CUDA library is not built / not loadable.  There is deliberately no CPU path."""
+
+
+def load() -> C.CDLL:
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise AlscoreUnavailable(
+            "%s not found: build it with `python -m semanticsegmentationactivelearning_b200.build` "
+            "(needs nvcc; the pool-scoring path has no CPU fallback)" % LIB_PATH)
+    try:
+        lib = C.CDLL(LIB_PATH)
+    except OSError as e:  # pragma: no cover
+        raise AlscoreUnavailable("cannot load %s: %s" % (LIB_PATH, e)) from e
+    for name, (res, args) in SIGNATURES.items():
+        fn = getattr(lib, name)  # AttributeError if the symbol is missing
+        fn.restype = res
+        fn.argtypes = args
+    _lib = lib
+    return lib
+
+
+def last_error(ctx=None) -> str:
+    msg = load().als_last_error(ctx)
+    return msg.decode("utf-8", "replace") if msg else ""
+
+
+def check(rc: int, ctx=None) -> None:
+    """Map als_status to the exception types the reference raises at the same places."""
+    if rc == ALS_OK:
+        return
+    msg = last_error(ctx) or last_error(None) or ("alscore error %d" % rc)
+    if rc == ALS_ERR_UNSUPPORTED:
+        raise NotImplementedError(msg)      # active_learning.py:259-260
+    if rc == ALS_ERR_INVALID:
+        raise ValueError(msg)
+    if rc == ALS_ERR_NOMEM:
+        raise MemoryError(msg)
+    raise RuntimeError(msg)

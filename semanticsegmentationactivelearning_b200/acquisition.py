@@ -1,0 +1,346 @@
+"""Host-side mirror of the reference's acquisition step, over the C ABI.
+
+The reference has no plugin interface: the "acquisition function" is the config string
+``alparams["measure"]`` (/root/reference/active_learning.py:240,252,256), the graph nodes
+``pseudo_confidence`` / ``pseudo_mean_confidence`` / ``pseudo_label`` / ``pseudo_mask``
+(:234-269) and the closure ``rank_confidence()`` (:682-715) with its return tuple
+``(low_conf_examples, unlabelled_confidence)``.  This module keeps those names, argument
+meanings and error behaviour; the arithmetic runs in libalscore.so on the GPU.
+
+PyTorch is used for device memory and streams only.  NumPy / host tensors are staged to the
+GPU by the library; nothing is ever scored on the CPU.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from typing import Iterable, Optional, Sequence, Tuple
+
+import numpy as np
+
+from . import _lib
+
+# alparams["measure"] values (conf/default_params.json:49) + the MC-dropout extension
+MEASURES = ("entropy", "margin", "confidence", "variance")
+
+
+def measure_id(name: str) -> int:
+    """Measure name -> C enum; unknown names raise exactly like active_learning.py:259-260."""
+    out = C.c_int(-1)
+    rc = _lib.load().als_measure_from_name(str(name).encode(), C.byref(out))
+    _lib.check(rc)
+    return out.value
+
+
+class _Logits:
+    """A borrowed view of a logits tensor: pointer + dtype + [T,N,H,W,C] + where it lives."""
+    __slots__ = ("ptr", "dtype", "T", "N", "H", "W", "C", "on_host", "keep", "device_index", "ndim")
+
+    def __init__(self, obj, dtype: Optional[str] = None):
+        self.keep = obj
+        self.device_index = None
+        torch = _torch()
+        if torch is not None and isinstance(obj, torch.Tensor):
+            if not obj.is_contiguous():
+                raise ValueError("logits must be dense C-contiguous NHWC (got a strided tensor)")
+            if obj.dtype == torch.float32:
+                self.dtype = _lib.ALS_F32
+            elif obj.dtype == torch.bfloat16:
+                self.dtype = _lib.ALS_BF16
+            else:
+                raise ValueError("logits dtype must be float32 or bfloat16, got %s" % obj.dtype)
+            self.on_host = not obj.is_cuda
+            if obj.is_cuda:
+                self.device_index = obj.device.index
+            self.ptr = obj.data_ptr()
+            shape = tuple(obj.shape)
+        elif isinstance(obj, np.ndarray):
+            if not obj.flags["C_CONTIGUOUS"]:
+                raise ValueError("logits must be dense C-contiguous NHWC (got a strided array)")
+            if obj.dtype == np.float32 and dtype in (None, "float32"):
+                self.dtype = _lib.ALS_F32
+            elif obj.dtype == np.uint16 and dtype == "bfloat16":
+                self.dtype = _lib.ALS_BF16      # bf16 bit patterns
+            else:
+                raise ValueError("logits dtype must be float32 (or uint16 bit patterns with dtype='bfloat16'), "
+                                 "got %s" % obj.dtype)
+            self.on_host = True
+            self.ptr = obj.ctypes.data
+            shape = obj.shape
+        else:
+            raise TypeError("logits must be a torch.Tensor or numpy.ndarray (use score_dlpack for other producers)")
+        self.ndim = len(shape)
+        if len(shape) == 4:
+            self.T = 1
+            self.N, self.H, self.W, self.C = (int(v) for v in shape)
+        elif len(shape) == 5:
+            self.T, self.N, self.H, self.W, self.C = (int(v) for v in shape)
+        else:
+            raise ValueError("logits must be [N,H,W,C] or [T,N,H,W,C], got shape %s" % (tuple(shape),))
+
+
+def _torch():
+    try:
+        import torch
+        return torch
+    except Exception:  # pragma: no cover
+        return None
+
+
+class Scorer:
+    """One alscore context (one GPU).  Not thread-safe; create one per thread / GPU."""
+
+    def __init__(self, device: Optional[int] = None, use_torch_stream: bool = True):
+        lib = _lib.load()
+        torch = _torch()
+        if device is None:
+            device = torch.cuda.current_device() if (torch is not None and torch.cuda.is_available()) else 0
+        self.device = int(device)
+        self._lib = lib
+        self._ctx = C.c_void_p()
+        _lib.check(lib.als_ctx_create(self.device, C.byref(self._ctx)))
+        self._stream = None
+        if use_torch_stream and torch is not None and torch.cuda.is_available():
+            # order our kernels after whatever produced the logits on torch's current stream
+            self._stream = int(torch.cuda.current_stream(self.device).cuda_stream)
+            _lib.check(lib.als_ctx_set_stream(self._ctx, C.c_void_p(self._stream)), self._ctx)
+
+    # -- lifetime ---------------------------------------------------------------------------
+    def close(self) -> None:
+        if getattr(self, "_ctx", None) is not None and self._ctx.value:
+            self._lib.als_ctx_destroy(self._ctx)
+            self._ctx = C.c_void_p()
+
+    def __del__(self):  # pragma: no cover
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *exc):
+        self.close()
+        return False
+
+    @property
+    def launch_count(self) -> int:
+        return int(self._lib.als_launch_count(self._ctx))
+
+    def _check(self, rc: int) -> None:
+        _lib.check(rc, self._ctx)
+
+    # -- graph-level boundary (active_learning.py:234-269) ---------------------------------
+    def score(self, logits, measure: str = "entropy", *, dtype: Optional[str] = None, out=None):
+        """pseudo_mean_confidence: per-image f64 mean confidence.
+
+        Device tensors are scored in place (zero copy) and the result is a torch.float64 CUDA
+        tensor (asynchronous); host arrays are staged and the result is a NumPy f64 array."""
+        m = measure_id(measure)
+        lg = _Logits(logits, dtype)
+        if lg.on_host:
+            scores = np.empty(lg.N, dtype=np.float64)
+            self._check(self._lib.als_score_host(self._ctx, lg.ptr, lg.dtype, lg.T, lg.N, lg.H, lg.W, lg.C, m,
+                                                 scores.ctypes.data, None, None, None, 0.0))
+            return scores
+        torch = _torch()
+        if out is None:
+            out = torch.empty(lg.N, dtype=torch.float64, device=logits.device)
+        stream = torch.cuda.current_stream(logits.device).cuda_stream
+        self._check(self._lib.als_score(self._ctx, lg.ptr, lg.dtype, lg.T, lg.N, lg.H, lg.W, lg.C, m,
+                                        out.data_ptr(), None, None, None, 0.0, C.c_void_p(stream)))
+        return out
+
+    def pseudo_annotation(self, logits, measure: str = "entropy", threshold: float = 0.9, *,
+                          dtype: Optional[str] = None, want_label: bool = True, want_mask: bool = True):
+        """The whole PseudoAnnotation scope in one pass: returns a dict with
+        pseudo_confidence f32[N,H,W], pseudo_mean_confidence f64[N], pseudo_label u8[N,H,W],
+        pseudo_mask u8[N,H,W] (conf < threshold ? 0 : 1)."""
+        m = measure_id(measure)
+        lg = _Logits(logits, dtype)
+        shp = (lg.N, lg.H, lg.W)
+        if lg.on_host:
+            conf = np.empty(shp, np.float32)
+            label = np.empty(shp, np.uint8) if want_label else None
+            mask = np.empty(shp, np.uint8) if want_mask else None
+            scores = np.empty(lg.N, np.float64)
+            self._check(self._lib.als_score_host(
+                self._ctx, lg.ptr, lg.dtype, lg.T, lg.N, lg.H, lg.W, lg.C, m, scores.ctypes.data, conf.ctypes.data,
+                label.ctypes.data if want_label else None, mask.ctypes.data if want_mask else None, float(threshold)))
+        else:
+            torch = _torch()
+            dev = logits.device
+            conf = torch.empty(shp, dtype=torch.float32, device=dev)
+            label = torch.empty(shp, dtype=torch.uint8, device=dev) if want_label else None
+            mask = torch.empty(shp, dtype=torch.uint8, device=dev) if want_mask else None
+            scores = torch.empty(lg.N, dtype=torch.float64, device=dev)
+            stream = torch.cuda.current_stream(dev).cuda_stream
+            self._check(self._lib.als_score(
+                self._ctx, lg.ptr, lg.dtype, lg.T, lg.N, lg.H, lg.W, lg.C, m, scores.data_ptr(), conf.data_ptr(),
+                label.data_ptr() if want_label else None, mask.data_ptr() if want_mask else None, float(threshold),
+                C.c_void_p(stream)))
+        return {"pseudo_confidence": conf, "pseudo_mean_confidence": scores, "pseudo_label": label,
+                "pseudo_mask": mask}
+
+    def score_dlpack(self, producer, measure: str = "entropy") -> np.ndarray:
+        """Score any ``__dlpack__`` producer (TF >= 2.2, CuPy, JAX, NumPy, torch): device tensors
+        zero-copy, host tensors staged.  Returns NumPy f64[N]."""
+        m = measure_id(measure)
+        capsule = producer.__dlpack__() if hasattr(producer, "__dlpack__") else producer
+        api = C.pythonapi
+        api.PyCapsule_GetPointer.restype = C.c_void_p
+        api.PyCapsule_GetPointer.argtypes = [C.py_object, C.c_char_p]
+        api.PyCapsule_IsValid.argtypes = [C.py_object, C.c_char_p]
+        api.PyCapsule_SetName.argtypes = [C.py_object, C.c_char_p]
+        if not api.PyCapsule_IsValid(capsule, b"dltensor"):
+            raise ValueError("expected a 'dltensor' DLPack capsule (already consumed or versioned capsule?)")
+        managed = api.PyCapsule_GetPointer(capsule, b"dltensor")
+        # read N for the output size: DLTensor.shape at offset 24, ndim at 16
+        ndim = C.c_int32.from_address(managed + 16).value
+        shape_ptr = C.c_void_p.from_address(managed + 24).value
+        if ndim not in (4, 5):
+            raise ValueError("logits must be [N,H,W,C] or [T,N,H,W,C], got ndim=%d" % ndim)
+        n = C.c_int64.from_address(shape_ptr + 8 * (ndim - 4)).value
+        scores = np.empty(max(n, 0), np.float64)
+        try:
+            self._check(self._lib.als_score_dlpack(self._ctx, managed, m, scores.ctypes.data))
+        finally:
+            # consumer protocol: mark the capsule used and run the producer's deleter
+            api.PyCapsule_SetName(capsule, _USED_NAME)
+            deleter = C.c_void_p.from_address(managed + 56).value
+            if deleter:
+                C.CFUNCTYPE(None, C.c_void_p)(deleter)(managed)
+        return scores
+
+    # -- loop-level boundary (rank_confidence, active_learning.py:682-715) ------------------
+    def pool_begin(self, num_examples: int) -> None:
+        self._check(self._lib.als_pool_begin(self._ctx, int(num_examples)))
+
+    def pool_score_batch(self, logits, batch_indices, measure: str = "entropy", *, dtype: Optional[str] = None) -> None:
+        m = measure_id(measure)
+        lg = _Logits(logits, dtype)
+        idx = np.ascontiguousarray(np.asarray(batch_indices, dtype=np.int64))
+        if idx.shape != (lg.N,):
+            raise ValueError("batch_indices must have one entry per image (%d), got shape %s" % (lg.N, idx.shape))
+        self._check(self._lib.als_pool_score_batch(self._ctx, lg.ptr, 1 if lg.on_host else 0, lg.dtype, lg.T, lg.N,
+                                                   lg.H, lg.W, lg.C, m, idx.ctypes.data))
+
+    def pool_scores(self, num_examples: int) -> np.ndarray:
+        out = np.empty(int(num_examples), np.float32)
+        self._check(self._lib.als_pool_scores(self._ctx, out.ctypes.data, int(num_examples)))
+        return out
+
+    def pool_select(self, unlabelled, selection_size: int) -> Tuple[np.ndarray, np.ndarray]:
+        unl = np.ascontiguousarray(np.asarray(unlabelled, dtype=np.int64))
+        if unl.ndim != 1:
+            raise ValueError("unlabelled must be a 1-D index array")
+        k = int(max(0, min(int(selection_size), unl.size)))
+        ids = np.empty(k, np.int64)
+        conf = np.empty(unl.size, np.float32)
+        cnt = C.c_int64(0)
+        self._check(self._lib.als_pool_select(self._ctx, unl.ctypes.data, unl.size, int(selection_size),
+                                              ids.ctypes.data, conf.ctypes.data, C.byref(cnt)))
+        return ids[:cnt.value], conf
+
+    # -- device primitives --------------------------------------------------------------------
+    def select_smallest(self, keys, ids, k: int):
+        """k smallest (key, id) pairs of CUDA tensors keys f32[M], ids i64[M] -> (keys, ids) ascending."""
+        torch = _torch()
+        if not (keys.is_cuda and ids.is_cuda and keys.dtype == torch.float32 and ids.dtype == torch.int64):
+            raise ValueError("keys must be a CUDA float32 tensor and ids a CUDA int64 tensor")
+        keys, ids = keys.contiguous(), ids.contiguous()
+        M = keys.numel()
+        if ids.numel() != M:
+            raise ValueError("keys and ids must have the same length")
+        kk = max(0, min(int(k), M))
+        ok = torch.empty(kk, dtype=torch.float32, device=keys.device)
+        oi = torch.empty(kk, dtype=torch.int64, device=keys.device)
+        stream = torch.cuda.current_stream(keys.device).cuda_stream
+        self._check(self._lib.als_select_smallest(self._ctx, keys.data_ptr(), ids.data_ptr(), M, int(k),
+                                                  ok.data_ptr(), oi.data_ptr(), C.c_void_p(stream)))
+        return ok, oi
+
+    def synth_logits(self, T: int, n0: int, n_imgs: int, H: int, W: int, C_: int, *, dtype: str = "float32",
+                     seed: int = 20191013, out=None, squeeze_t: bool = True):
+        """Device twin of oracle/synth.py: images n0..n0+n_imgs-1 of the synthetic pool."""
+        torch = _torch()
+        tdt = {"float32": torch.float32, "bfloat16": torch.bfloat16}[dtype]
+        if out is None:
+            out = torch.empty((T, n_imgs, H, W, C_), dtype=tdt, device=torch.device("cuda", self.device))
+        stream = torch.cuda.current_stream(out.device).cuda_stream
+        self._check(self._lib.als_synth_logits(self._ctx, out.data_ptr(), _lib.ALS_F32 if dtype == "float32" else _lib.ALS_BF16,
+                                               T, n0, n_imgs, H, W, C_, seed, 1 if T > 1 else 0, C.c_void_p(stream)))
+        return out[0] if (T == 1 and squeeze_t and out.dim() == 5) else out
+
+    def flush_l2(self) -> None:
+        torch = _torch()
+        stream = torch.cuda.current_stream(self.device).cuda_stream
+        self._check(self._lib.als_flush_l2(self._ctx, C.c_void_p(stream)))
+
+    def describe_launch(self, dtype: str, T: int, N: int, H: int, W: int, C_: int, measure: str) -> dict:
+        name = C.create_string_buffer(128)
+        g, b, s, st, tp = (C.c_int() for _ in range(5))
+        self._check(self._lib.als_describe_launch(self._ctx, _lib.ALS_F32 if dtype == "float32" else _lib.ALS_BF16, T, N, H, W,
+                                                  C_, measure_id(measure), name, C.byref(g), C.byref(b), C.byref(s),
+                                                  C.byref(st), C.byref(tp)))
+        return {"kernel": name.value.decode(), "grid": g.value, "block": b.value, "smem_bytes": s.value,
+                "stages": st.value, "tile_pixels": tp.value}
+
+
+_USED_NAME = b"used_dltensor"   # module-level: PyCapsule_SetName keeps the pointer, not a copy
+
+_default_scorers = {}
+
+
+def default_scorer(device: Optional[int] = None) -> Scorer:
+    torch = _torch()
+    if device is None:
+        device = torch.cuda.current_device() if (torch is not None and torch.cuda.is_available()) else 0
+    sc = _default_scorers.get(device)
+    if sc is None:
+        sc = _default_scorers[device] = Scorer(device)
+    return sc
+
+
+def _slice_images(logits, sl: slice):
+    return logits[sl] if logits.ndim == 4 else logits[:, sl]
+
+
+def rank_confidence(logits, unlabelled, selection_size: int, measure: str = "entropy", *,
+                    batch_size: Optional[int] = None, example_index=None, num_examples: Optional[int] = None,
+                    dtype: Optional[str] = None, scorer: Optional[Scorer] = None):
+    """Drop-in for the ``rank_confidence()`` closure (active_learning.py:682-715).
+
+    logits            the pool's logits [N,H,W,C] / [T,N,H,W,C] (device or host), or an iterable of
+                      ``(batch_logits, batch_indices)`` pairs as ``sess.run`` would hand them out (:697-698)
+    unlabelled        index array into the example list (:705)
+    selection_size    alparams["selection_size"] (:708); must be > 0 like at the call site (:779)
+    Returns ``(low_conf_examples, unlabelled_confidence)`` (:715): the min(len(unlabelled),
+    selection_size) lowest-confidence example ids (ascending confidence, ties by id) and the
+    float32 confidences of all unlabelled examples (examples never visited keep 0.0, :685).
+    """
+    sc = scorer or default_scorer()
+    measure_id(measure)   # unknown measure fails before any work, like graph construction does
+    unlabelled = np.asarray(unlabelled, dtype=np.int64)
+    if hasattr(logits, "ndim") and hasattr(logits, "shape"):
+        n = int(logits.shape[-4])
+        if example_index is None:
+            example_index = np.arange(n, dtype=np.int64)
+        example_index = np.asarray(example_index, dtype=np.int64)
+        if num_examples is None:
+            num_examples = int(max(example_index.max(initial=-1), unlabelled.max(initial=-1))) + 1
+        bs = n if not batch_size else int(batch_size)
+        batches = ((_slice_images(logits, slice(i, i + bs)), example_index[i:i + bs]) for i in range(0, n, max(bs, 1)))
+        if logits.ndim == 5 and bs < n and not getattr(logits, "is_cuda", False):
+            # a [T, batch] slice of a host array is strided: make each batch dense before staging
+            batches = ((np.ascontiguousarray(b) if isinstance(b, np.ndarray) else b.contiguous(), i) for b, i in batches)
+        elif logits.ndim == 5 and bs < n:
+            batches = ((b.contiguous(), i) for b, i in batches)
+    else:
+        batches = logits
+        if num_examples is None:
+            raise ValueError("num_examples is required when logits is an iterable of batches")
+    sc.pool_begin(int(num_examples))
+    for batch_logits, batch_indices in batches:
+        sc.pool_score_batch(batch_logits, batch_indices, measure, dtype=dtype)
+    return sc.pool_select(unlabelled, selection_size)

@@ -1,0 +1,697 @@
+// C ABI of the pool-scoring path (include/alscore.h): contexts, validation, host staging,
+// DLPack borrowing, the rank_confidence-shaped pool API.
+#include <cuda_runtime.h>
+#include <math.h>
+#include <stdarg.h>
+#include <stdio.h>
+#include <string.h>
+
+#include <string>
+#include <vector>
+
+#include "../../include/alscore.h"
+#include "score.cuh"
+#include "select.cuh"
+#include "synth.cuh"
+
+// ---- minimal DLPack v0.x ABI mirror (dlpack.h: DLDevice, DLDataType, DLTensor, DLManagedTensor)
+extern "C" {
+typedef struct { int32_t device_type; int32_t device_id; } AlsDLDevice;
+typedef struct { uint8_t code; uint8_t bits; uint16_t lanes; } AlsDLDataType;
+typedef struct {
+  void* data; AlsDLDevice device; int32_t ndim; AlsDLDataType dtype;
+  int64_t* shape; int64_t* strides; uint64_t byte_offset;
+} AlsDLTensor;
+typedef struct AlsDLManagedTensor {
+  AlsDLTensor dl_tensor; void* manager_ctx; void (*deleter)(struct AlsDLManagedTensor*);
+} AlsDLManagedTensor;
+}
+static_assert(sizeof(AlsDLTensor) == 48, "DLTensor ABI");
+enum { kAlsDLCPU = 1, kAlsDLCUDA = 2, kAlsDLCUDAHost = 3, kAlsDLCUDAManaged = 13 };
+enum { kAlsDLFloat = 2, kAlsDLBfloat = 4 };
+
+static thread_local std::string g_tls_error;
+
+struct als_ctx {
+  int device = 0;
+  int num_sms = 148;
+  int max_smem = 227 * 1024;
+  cudaStream_t stream = nullptr;
+  bool owns_stream = true;
+  cudaStream_t copy_stream = nullptr;
+  std::string error;
+  int64_t launches = 0;
+  // per-image fixed-point accumulators
+  long long* acc = nullptr;
+  unsigned int* flags = nullptr;
+  int64_t acc_cap = 0;
+  // device scratch for scores / indices
+  double* scores_dev = nullptr;
+  int64_t scores_cap = 0;
+  long long* index_dev = nullptr;
+  int64_t index_cap = 0;
+  // pool state (rank_confidence)
+  float* pool32 = nullptr;
+  int64_t pool_n = -1;
+  int64_t pool_cap = 0;
+  // selection scratch
+  long long* sel_ids = nullptr;
+  float* sel_keys = nullptr;
+  float* sel_tmp_keys = nullptr;
+  long long* sel_tmp_ids = nullptr;
+  float* sel_out_keys = nullptr;
+  long long* sel_out_ids = nullptr;
+  int64_t sel_cap = 0;
+  // host -> device staging (double buffered)
+  void* stage[2] = {nullptr, nullptr};
+  size_t stage_cap = 0;
+  cudaEvent_t ev_copied[2] = {nullptr, nullptr};
+  cudaEvent_t ev_scored[2] = {nullptr, nullptr};
+  int stage_next = 0;
+  // per-pixel output staging for the host path
+  void* maps_dev = nullptr;
+  size_t maps_cap = 0;
+  // L2 flush scratch
+  void* flush_buf = nullptr;
+  size_t flush_bytes = 0;
+};
+
+namespace {
+
+int fail(als_ctx* ctx, int code, const char* fmt, ...) {
+  char buf[512];
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(buf, sizeof(buf), fmt, ap);
+  va_end(ap);
+  g_tls_error = buf;
+  if (ctx) ctx->error = buf;
+  return code;
+}
+
+#define ALS_CUDA(ctx, call)                                                                             \
+  do {                                                                                                  \
+    cudaError_t _e = (call);                                                                            \
+    if (_e != cudaSuccess) {                                                                            \
+      (void)cudaGetLastError();                                                                         \
+      return fail(ctx, _e == cudaErrorMemoryAllocation ? ALS_ERR_NOMEM : ALS_ERR_CUDA, "%s failed: %s", \
+                  #call, cudaGetErrorString(_e));                                                       \
+    }                                                                                                   \
+  } while (0)
+
+#define ALS_TRY(expr)            \
+  do {                           \
+    int _rc = (expr);            \
+    if (_rc != ALS_OK) return _rc; \
+  } while (0)
+
+struct DeviceGuard {
+  int prev = -1;
+  explicit DeviceGuard(int dev) {
+    cudaGetDevice(&prev);
+    if (prev != dev) cudaSetDevice(dev);
+    else prev = -1;
+  }
+  ~DeviceGuard() {
+    if (prev >= 0) cudaSetDevice(prev);
+  }
+};
+
+template <typename T>
+int grow(als_ctx* ctx, T** ptr, int64_t* cap, int64_t need, bool zero) {
+  if (need <= *cap) return ALS_OK;
+  int64_t n = *cap > 0 ? *cap : 1024;
+  while (n < need) n *= 2;
+  ALS_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+  if (*ptr) ALS_CUDA(ctx, cudaFree(*ptr));
+  *ptr = nullptr;
+  *cap = 0;
+  ALS_CUDA(ctx, cudaMalloc(reinterpret_cast<void**>(ptr), static_cast<size_t>(n) * sizeof(T)));
+  if (zero) ALS_CUDA(ctx, cudaMemsetAsync(*ptr, 0, static_cast<size_t>(n) * sizeof(T), ctx->stream));
+  *cap = n;
+  return ALS_OK;
+}
+
+int grow_bytes(als_ctx* ctx, void** ptr, size_t* cap, size_t need) {
+  if (need <= *cap) return ALS_OK;
+  ALS_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+  if (*ptr) ALS_CUDA(ctx, cudaFree(*ptr));
+  *ptr = nullptr;
+  *cap = 0;
+  ALS_CUDA(ctx, cudaMalloc(ptr, need));
+  *cap = need;
+  return ALS_OK;
+}
+
+int ceil_log2_ll(long long v) {
+  int b = 0;
+  while ((1ll << b) < v) ++b;
+  return b;
+}
+
+struct Shape {
+  int64_t T, N, H, W, C;
+  int64_t P() const { return H * W; }
+  int64_t elems() const { return T * N * H * W * C; }
+};
+
+int check_common(als_ctx* ctx, const void* logits, int dtype, const Shape& s, int measure, bool want_label) {
+  if (!ctx) return fail(nullptr, ALS_ERR_INVALID, "context is NULL");
+  if (dtype != ALS_F32 && dtype != ALS_BF16) return fail(ctx, ALS_ERR_INVALID, "logits dtype must be float32 or bfloat16");
+  if (measure < ALS_ENTROPY || measure > ALS_VARIANCE)
+    return fail(ctx, ALS_ERR_UNSUPPORTED, "Uncertainty function not implemented.");
+  if (s.T < 1 || s.N < 0 || s.H < 1 || s.W < 1) return fail(ctx, ALS_ERR_INVALID, "bad logits shape [T=%lld,N=%lld,H=%lld,W=%lld,C=%lld]",
+                                                            (long long)s.T, (long long)s.N, (long long)s.H, (long long)s.W, (long long)s.C);
+  if (s.C < 2) return fail(ctx, ALS_ERR_INVALID, "need at least 2 classes, got C=%lld", (long long)s.C);
+  if (s.C > 65536) return fail(ctx, ALS_ERR_INVALID, "C=%lld is too large", (long long)s.C);
+  if (measure == ALS_VARIANCE && s.T < 2) return fail(ctx, ALS_ERR_INVALID, "measure 'variance' needs T >= 2 Monte-Carlo samples");
+  if (want_label && s.C > 256) return fail(ctx, ALS_ERR_INVALID, "uint8 pseudo_label needs C <= 256");
+  if (s.P() > (1ll << 40)) return fail(ctx, ALS_ERR_INVALID, "image too large");
+  if (s.N > 0x7fffffff) return fail(ctx, ALS_ERR_INVALID, "too many images in one call");
+  if (s.N > 0 && !logits) return fail(ctx, ALS_ERR_INVALID, "logits pointer is NULL");
+  if (reinterpret_cast<uintptr_t>(logits) % 16 != 0) return fail(ctx, ALS_ERR_INVALID, "logits must be 16-byte aligned");
+  return ALS_OK;
+}
+
+int check_device_ptr(als_ctx* ctx, const void* p, const char* what) {
+  if (!p) return ALS_OK;
+  cudaPointerAttributes a;
+  cudaError_t e = cudaPointerGetAttributes(&a, p);
+  if (e != cudaSuccess) {
+    (void)cudaGetLastError();
+    return fail(ctx, ALS_ERR_INVALID, "%s: not a CUDA pointer (%s)", what, cudaGetErrorString(e));
+  }
+  if (a.type != cudaMemoryTypeDevice && a.type != cudaMemoryTypeManaged)
+    return fail(ctx, ALS_ERR_INVALID, "%s must be device memory (use the *_host entry for host memory)", what);
+  if (a.type == cudaMemoryTypeDevice && a.device != ctx->device)
+    return fail(ctx, ALS_ERR_INVALID, "%s lives on GPU %d but the context is bound to GPU %d", what, a.device, ctx->device);
+  return ALS_OK;
+}
+
+// Core: device logits -> fixed-point sums -> finalize.  scores64 / pool scatter optional.
+int score_device(als_ctx* ctx, const void* logits, int dtype, const Shape& s, int measure, double* scores64,
+                 float* pool32, const long long* example_index_dev, int64_t num_examples, float* conf_map,
+                 uint8_t* label, uint8_t* mask, float threshold, cudaStream_t stream) {
+  if (s.N == 0) return ALS_OK;
+  const long long P = s.P();
+  const int es = dtype == ALS_F32 ? 4 : 2;
+  const long long sample_stride = s.N * P * s.C;
+  const bool aligned = (s.T == 1) || ((sample_stride * es) % 16 == 0);
+  als::LaunchPlan plan = als::plan_score(dtype, static_cast<int>(s.C), measure, static_cast<int>(s.T), s.N * P, aligned,
+                                         ctx->num_sms, ctx->max_smem);
+  int shift = 62 - ceil_log2_ll(P);
+  if (shift > 44) shift = 44;
+  als::ScoreParams p{};
+  p.logits = logits;
+  p.sample_stride = sample_stride;
+  p.total_pixels = s.N * P;
+  p.P = P;
+  p.T = static_cast<int>(s.T);
+  p.C = static_cast<int>(s.C);
+  p.measure = measure;
+  p.inv_log_c = 1.0f / logf(static_cast<float>(s.C));
+  p.threshold = threshold;
+  p.inv_T = 1.0f / static_cast<float>(s.T);
+  p.fx_scale = ldexpf(1.0f, shift);
+  p.acc = ctx->acc;
+  p.flags = ctx->flags;
+  p.conf_map = conf_map;
+  p.label = label;
+  p.mask = mask;
+  ALS_CUDA(ctx, als::launch_score(plan, dtype, p, stream));
+  ALS_CUDA(ctx, als::launch_finalize(ctx->acc, ctx->flags, static_cast<int>(s.N), ldexp(1.0, -shift) / static_cast<double>(P),
+                                     scores64, pool32, example_index_dev, num_examples, stream));
+  ctx->launches += 2;
+  return ALS_OK;
+}
+
+int ensure_acc(als_ctx* ctx, int64_t n) {
+  if (n <= ctx->acc_cap) return ALS_OK;
+  int64_t cap = ctx->acc_cap > 0 ? ctx->acc_cap : 1024;
+  while (cap < n) cap *= 2;
+  ALS_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+  if (ctx->acc) ALS_CUDA(ctx, cudaFree(ctx->acc));
+  if (ctx->flags) ALS_CUDA(ctx, cudaFree(ctx->flags));
+  ctx->acc = nullptr;
+  ctx->flags = nullptr;
+  ctx->acc_cap = 0;
+  ALS_CUDA(ctx, cudaMalloc(reinterpret_cast<void**>(&ctx->acc), static_cast<size_t>(cap) * sizeof(long long)));
+  ALS_CUDA(ctx, cudaMalloc(reinterpret_cast<void**>(&ctx->flags), static_cast<size_t>(cap) * sizeof(unsigned int)));
+  ALS_CUDA(ctx, cudaMemset(ctx->acc, 0, static_cast<size_t>(cap) * sizeof(long long)));
+  ALS_CUDA(ctx, cudaMemset(ctx->flags, 0, static_cast<size_t>(cap) * sizeof(unsigned int)));
+  ctx->acc_cap = cap;
+  return ALS_OK;
+}
+
+constexpr size_t kStageDefault = 256ull << 20;
+
+int ensure_stage(als_ctx* ctx, size_t need) {
+  if (need <= ctx->stage_cap) return ALS_OK;
+  size_t cap = ctx->stage_cap ? ctx->stage_cap : kStageDefault;
+  while (cap < need) cap *= 2;
+  ALS_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+  ALS_CUDA(ctx, cudaStreamSynchronize(ctx->copy_stream));
+  for (int b = 0; b < 2; ++b) {
+    if (ctx->stage[b]) ALS_CUDA(ctx, cudaFree(ctx->stage[b]));
+    ctx->stage[b] = nullptr;
+  }
+  ctx->stage_cap = 0;
+  for (int b = 0; b < 2; ++b) ALS_CUDA(ctx, cudaMalloc(&ctx->stage[b], cap));
+  ctx->stage_cap = cap;
+  return ALS_OK;
+}
+
+// Stage images [n0, n0+nb) of host logits [T,N,P,C] into a staging buffer as [T,nb,P,C]; returns the buffer index.
+int stage_chunk(als_ctx* ctx, const unsigned char* host, const Shape& s, int es, int64_t n0, int64_t nb, int* buf_out) {
+  const int b = ctx->stage_next;
+  ctx->stage_next ^= 1;
+  const size_t img_bytes = static_cast<size_t>(s.P()) * s.C * es;
+  // the previous user of this buffer must have been scored
+  ALS_CUDA(ctx, cudaStreamWaitEvent(ctx->copy_stream, ctx->ev_scored[b], 0));
+  for (int64_t t = 0; t < s.T; ++t) {
+    const unsigned char* src = host + (static_cast<size_t>(t) * s.N + n0) * img_bytes;
+    unsigned char* dst = static_cast<unsigned char*>(ctx->stage[b]) + static_cast<size_t>(t) * nb * img_bytes;
+    ALS_CUDA(ctx, cudaMemcpyAsync(dst, src, static_cast<size_t>(nb) * img_bytes, cudaMemcpyHostToDevice, ctx->copy_stream));
+  }
+  ALS_CUDA(ctx, cudaEventRecord(ctx->ev_copied[b], ctx->copy_stream));
+  *buf_out = b;
+  return ALS_OK;
+}
+
+}  // namespace
+
+// ---------------------------------------------------------------------------------------------
+extern "C" {
+
+int als_version(void) { return ALS_VERSION; }
+
+int als_device_count(void) {
+  int n = 0;
+  cudaError_t e = cudaGetDeviceCount(&n);
+  if (e != cudaSuccess) {
+    (void)cudaGetLastError();
+    return fail(nullptr, ALS_ERR_CUDA, "cudaGetDeviceCount failed: %s", cudaGetErrorString(e));
+  }
+  return n;
+}
+
+const char* als_last_error(const als_ctx* ctx) { return ctx ? ctx->error.c_str() : g_tls_error.c_str(); }
+
+int als_measure_from_name(const char* name, int* measure) {
+  if (!name || !measure) return fail(nullptr, ALS_ERR_INVALID, "NULL argument");
+  static const char* names[] = {"entropy", "margin", "confidence", "variance"};
+  for (int i = 0; i < 4; ++i)
+    if (strcmp(name, names[i]) == 0) {
+      *measure = i;
+      return ALS_OK;
+    }
+  // active_learning.py:259-260
+  return fail(nullptr, ALS_ERR_UNSUPPORTED, "Uncertainty function not implemented.");
+}
+
+int als_ctx_create(int device, als_ctx** out) {
+  if (!out) return fail(nullptr, ALS_ERR_INVALID, "out is NULL");
+  *out = nullptr;
+  int n = 0;
+  cudaError_t e = cudaGetDeviceCount(&n);
+  if (e != cudaSuccess || n == 0) {
+    (void)cudaGetLastError();
+    return fail(nullptr, ALS_ERR_CUDA, "no CUDA device available (%s); alscore has no CPU fallback",
+                e == cudaSuccess ? "device count is 0" : cudaGetErrorString(e));
+  }
+  if (device < 0 || device >= n) return fail(nullptr, ALS_ERR_INVALID, "device %d out of range [0, %d)", device, n);
+  als_ctx* ctx = new als_ctx();
+  ctx->device = device;
+  DeviceGuard g(device);
+  cudaDeviceProp prop;
+  e = cudaGetDeviceProperties(&prop, device);
+  if (e != cudaSuccess) {
+    delete ctx;
+    return fail(nullptr, ALS_ERR_CUDA, "cudaGetDeviceProperties failed: %s", cudaGetErrorString(e));
+  }
+  if (prop.major != 10) {
+    delete ctx;
+    return fail(nullptr, ALS_ERR_CUDA, "alscore kernels are built for sm_100a (B200); device %d is sm_%d%d", device,
+                prop.major, prop.minor);
+  }
+  ctx->num_sms = prop.multiProcessorCount;
+  ctx->max_smem = static_cast<int>(prop.sharedMemPerBlockOptin);
+  bool ok = cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking) == cudaSuccess &&
+            cudaStreamCreateWithFlags(&ctx->copy_stream, cudaStreamNonBlocking) == cudaSuccess;
+  for (int b = 0; b < 2 && ok; ++b) {
+    ok = cudaEventCreateWithFlags(&ctx->ev_copied[b], cudaEventDisableTiming) == cudaSuccess &&
+         cudaEventCreateWithFlags(&ctx->ev_scored[b], cudaEventDisableTiming) == cudaSuccess;
+  }
+  if (!ok) {
+    (void)cudaGetLastError();
+    als_ctx_destroy(ctx);
+    return fail(nullptr, ALS_ERR_CUDA, "failed to create streams/events");
+  }
+  *out = ctx;
+  return ALS_OK;
+}
+
+int als_ctx_destroy(als_ctx* ctx) {
+  if (!ctx) return ALS_OK;
+  DeviceGuard g(ctx->device);
+  if (ctx->stream) cudaStreamSynchronize(ctx->stream);
+  if (ctx->copy_stream) cudaStreamSynchronize(ctx->copy_stream);
+  void* ptrs[] = {ctx->acc, ctx->flags, ctx->scores_dev, ctx->index_dev, ctx->pool32, ctx->sel_ids, ctx->sel_keys,
+                  ctx->sel_tmp_keys, ctx->sel_tmp_ids, ctx->sel_out_keys, ctx->sel_out_ids, ctx->stage[0], ctx->stage[1],
+                  ctx->maps_dev, ctx->flush_buf};
+  for (void* p : ptrs)
+    if (p) cudaFree(p);
+  for (int b = 0; b < 2; ++b) {
+    if (ctx->ev_copied[b]) cudaEventDestroy(ctx->ev_copied[b]);
+    if (ctx->ev_scored[b]) cudaEventDestroy(ctx->ev_scored[b]);
+  }
+  if (ctx->stream && ctx->owns_stream) cudaStreamDestroy(ctx->stream);
+  if (ctx->copy_stream) cudaStreamDestroy(ctx->copy_stream);
+  (void)cudaGetLastError();
+  delete ctx;
+  return ALS_OK;
+}
+
+int64_t als_launch_count(const als_ctx* ctx) { return ctx ? ctx->launches : 0; }
+
+int als_ctx_set_stream(als_ctx* ctx, void* stream) {
+  if (!ctx) return fail(nullptr, ALS_ERR_INVALID, "context is NULL");
+  DeviceGuard g(ctx->device);
+  ALS_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+  if (ctx->owns_stream && ctx->stream) ALS_CUDA(ctx, cudaStreamDestroy(ctx->stream));
+  ctx->stream = static_cast<cudaStream_t>(stream);
+  ctx->owns_stream = false;
+  return ALS_OK;
+}
+
+int als_score(als_ctx* ctx, const void* logits, int dtype, int64_t T, int64_t N, int64_t H, int64_t W, int64_t C,
+              int measure, double* scores, float* conf_map, uint8_t* label, uint8_t* mask, float threshold,
+              void* stream) {
+  const Shape s{T, N, H, W, C};
+  ALS_TRY(check_common(ctx, logits, dtype, s, measure, label != nullptr));
+  if (N > 0 && !scores) return fail(ctx, ALS_ERR_INVALID, "scores pointer is NULL");
+  DeviceGuard g(ctx->device);
+  if (N > 0) {
+    ALS_TRY(check_device_ptr(ctx, logits, "logits"));
+    ALS_TRY(check_device_ptr(ctx, scores, "scores"));
+    ALS_TRY(check_device_ptr(ctx, conf_map, "conf_map"));
+    ALS_TRY(check_device_ptr(ctx, label, "label"));
+    ALS_TRY(check_device_ptr(ctx, mask, "mask"));
+  }
+  ALS_TRY(ensure_acc(ctx, N));
+  cudaStream_t st = stream ? static_cast<cudaStream_t>(stream) : ctx->stream;
+  return score_device(ctx, logits, dtype, s, measure, scores, nullptr, nullptr, 0, conf_map, label, mask, threshold, st);
+}
+
+int als_score_host(als_ctx* ctx, const void* logits, int dtype, int64_t T, int64_t N, int64_t H, int64_t W, int64_t C,
+                   int measure, double* scores, float* conf_map, uint8_t* label, uint8_t* mask, float threshold) {
+  const Shape s{T, N, H, W, C};
+  ALS_TRY(check_common(ctx, logits, dtype, s, measure, label != nullptr));
+  if (N == 0) return ALS_OK;
+  if (!scores) return fail(ctx, ALS_ERR_INVALID, "scores pointer is NULL");
+  DeviceGuard g(ctx->device);
+  const int es = dtype == ALS_F32 ? 4 : 2;
+  const size_t img_bytes = static_cast<size_t>(s.P()) * C * es;
+  const size_t per_img_all_t = img_bytes * T;
+  int64_t nb_max = static_cast<int64_t>(kStageDefault / per_img_all_t);
+  if (nb_max < 1) nb_max = 1;
+  if (nb_max > N) nb_max = N;
+  // keep every sample plane of a chunk 16-byte aligned inside the staging buffer
+  ALS_TRY(ensure_stage(ctx, static_cast<size_t>(nb_max) * per_img_all_t));
+  ALS_TRY(ensure_acc(ctx, nb_max));
+  ALS_TRY(grow(ctx, &ctx->scores_dev, &ctx->scores_cap, N, false));
+  const bool maps = conf_map || label || mask;
+  const size_t P = static_cast<size_t>(s.P());
+  if (maps) ALS_TRY(grow_bytes(ctx, &ctx->maps_dev, &ctx->maps_cap, static_cast<size_t>(nb_max) * P * 6));
+  const unsigned char* host = static_cast<const unsigned char*>(logits);
+  for (int64_t n0 = 0; n0 < N; n0 += nb_max) {
+    const int64_t nb = (N - n0) < nb_max ? (N - n0) : nb_max;
+    int b = 0;
+    ALS_TRY(stage_chunk(ctx, host, s, es, n0, nb, &b));
+    ALS_CUDA(ctx, cudaStreamWaitEvent(ctx->stream, ctx->ev_copied[b], 0));
+    float* d_conf = nullptr;
+    uint8_t* d_label = nullptr;
+    uint8_t* d_mask = nullptr;
+    if (maps) {
+      unsigned char* m = static_cast<unsigned char*>(ctx->maps_dev);
+      if (conf_map) d_conf = reinterpret_cast<float*>(m);
+      if (label) d_label = m + static_cast<size_t>(nb_max) * P * 4;
+      if (mask) d_mask = m + static_cast<size_t>(nb_max) * P * 5;
+    }
+    const Shape cs{T, nb, H, W, C};
+    ALS_TRY(score_device(ctx, ctx->stage[b], dtype, cs, measure, ctx->scores_dev + n0, nullptr, nullptr, 0, d_conf,
+                         d_label, d_mask, threshold, ctx->stream));
+    ALS_CUDA(ctx, cudaEventRecord(ctx->ev_scored[b], ctx->stream));
+    if (d_conf) ALS_CUDA(ctx, cudaMemcpyAsync(conf_map + n0 * P, d_conf, nb * P * 4, cudaMemcpyDeviceToHost, ctx->stream));
+    if (d_label) ALS_CUDA(ctx, cudaMemcpyAsync(label + n0 * P, d_label, nb * P, cudaMemcpyDeviceToHost, ctx->stream));
+    if (d_mask) ALS_CUDA(ctx, cudaMemcpyAsync(mask + n0 * P, d_mask, nb * P, cudaMemcpyDeviceToHost, ctx->stream));
+  }
+  ALS_CUDA(ctx, cudaMemcpyAsync(scores, ctx->scores_dev, static_cast<size_t>(N) * sizeof(double), cudaMemcpyDeviceToHost,
+                                ctx->stream));
+  ALS_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+  return ALS_OK;
+}
+
+int als_score_dlpack(als_ctx* ctx, void* managed, int measure, double* scores) {
+  if (!ctx) return fail(nullptr, ALS_ERR_INVALID, "context is NULL");
+  if (!managed) return fail(ctx, ALS_ERR_INVALID, "DLManagedTensor is NULL");
+  const AlsDLTensor& t = static_cast<AlsDLManagedTensor*>(managed)->dl_tensor;
+  int dtype;
+  if (t.dtype.lanes != 1) return fail(ctx, ALS_ERR_INVALID, "vector dtypes are not supported");
+  if (t.dtype.code == kAlsDLFloat && t.dtype.bits == 32) dtype = ALS_F32;
+  else if (t.dtype.code == kAlsDLBfloat && t.dtype.bits == 16) dtype = ALS_BF16;
+  else return fail(ctx, ALS_ERR_INVALID, "logits dtype must be float32 or bfloat16 (DLPack code %d, bits %d)", t.dtype.code, t.dtype.bits);
+  if (t.ndim != 4 && t.ndim != 5) return fail(ctx, ALS_ERR_INVALID, "logits must be [N,H,W,C] or [T,N,H,W,C], got ndim=%d", t.ndim);
+  const int64_t* sh = t.shape;
+  const int o = t.ndim - 4;
+  const Shape s{o ? sh[0] : 1, sh[o], sh[o + 1], sh[o + 2], sh[o + 3]};
+  if (t.strides) {  // must be dense C-order (NHWC, class innermost)
+    int64_t expect = 1;
+    for (int d = t.ndim - 1; d >= 0; --d) {
+      if (sh[d] != 1 && t.strides[d] != expect)
+        return fail(ctx, ALS_ERR_INVALID, "logits must be dense C-contiguous NHWC (stride[%d]=%lld, expected %lld)", d,
+                    (long long)t.strides[d], (long long)expect);
+      expect *= sh[d];
+    }
+  }
+  const void* data = static_cast<const unsigned char*>(t.data) + t.byte_offset;
+  if (!scores) return fail(ctx, ALS_ERR_INVALID, "scores pointer is NULL");
+  switch (t.device.device_type) {
+    case kAlsDLCUDA:
+    case kAlsDLCUDAManaged: {
+      if (t.device.device_type == kAlsDLCUDA && t.device.device_id != ctx->device)
+        return fail(ctx, ALS_ERR_INVALID, "logits live on GPU %d but the context is bound to GPU %d", t.device.device_id,
+                    ctx->device);
+      ALS_TRY(check_common(ctx, data, dtype, s, measure, false));
+      if (s.N == 0) return ALS_OK;
+      DeviceGuard g(ctx->device);
+      ALS_TRY(ensure_acc(ctx, s.N));
+      ALS_TRY(grow(ctx, &ctx->scores_dev, &ctx->scores_cap, s.N, false));
+      // The producer's work may still be in flight on its own stream: order behind everything on the device.
+      ALS_CUDA(ctx, cudaDeviceSynchronize());
+      ALS_TRY(score_device(ctx, data, dtype, s, measure, ctx->scores_dev, nullptr, nullptr, 0, nullptr, nullptr, nullptr,
+                           0.f, ctx->stream));
+      ALS_CUDA(ctx, cudaMemcpyAsync(scores, ctx->scores_dev, static_cast<size_t>(s.N) * sizeof(double),
+                                    cudaMemcpyDeviceToHost, ctx->stream));
+      ALS_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+      return ALS_OK;
+    }
+    case kAlsDLCPU:
+    case kAlsDLCUDAHost:
+      return als_score_host(ctx, data, dtype, s.T, s.N, s.H, s.W, s.C, measure, scores, nullptr, nullptr, nullptr, 0.f);
+    default:
+      return fail(ctx, ALS_ERR_INVALID, "unsupported DLPack device type %d", t.device.device_type);
+  }
+}
+
+// ---- rank_confidence-shaped pool API -----------------------------------------------------------
+
+int als_pool_begin(als_ctx* ctx, int64_t num_examples) {
+  if (!ctx) return fail(nullptr, ALS_ERR_INVALID, "context is NULL");
+  if (num_examples < 0) return fail(ctx, ALS_ERR_INVALID, "num_examples must be >= 0");
+  DeviceGuard g(ctx->device);
+  ALS_TRY(grow(ctx, &ctx->pool32, &ctx->pool_cap, num_examples > 0 ? num_examples : 1, false));
+  // :685  np.zeros(num_examples, dtype=np.float32)
+  ALS_CUDA(ctx, cudaMemsetAsync(ctx->pool32, 0, static_cast<size_t>(ctx->pool_cap) * sizeof(float), ctx->stream));
+  ctx->pool_n = num_examples;
+  return ALS_OK;
+}
+
+int als_pool_score_batch(als_ctx* ctx, const void* logits, int logits_on_host, int dtype, int64_t T, int64_t B,
+                         int64_t H, int64_t W, int64_t C, int measure, const int64_t* example_index) {
+  const Shape s{T, B, H, W, C};
+  ALS_TRY(check_common(ctx, logits, dtype, s, measure, false));
+  if (ctx->pool_n < 0) return fail(ctx, ALS_ERR_STATE, "als_pool_begin has not been called");
+  if (B == 0) return ALS_OK;
+  if (!example_index) return fail(ctx, ALS_ERR_INVALID, "example_index is NULL");
+  for (int64_t i = 0; i < B; ++i)
+    if (example_index[i] < 0 || example_index[i] >= ctx->pool_n)
+      return fail(ctx, ALS_ERR_INVALID, "example_index[%lld]=%lld out of range [0, %lld)", (long long)i,
+                  (long long)example_index[i], (long long)ctx->pool_n);
+  DeviceGuard g(ctx->device);
+  ALS_TRY(ensure_acc(ctx, B));
+  ALS_TRY(grow(ctx, &ctx->index_dev, &ctx->index_cap, B, false));
+  static_assert(sizeof(long long) == sizeof(int64_t), "");
+  const void* dev_logits = logits;
+  int b = -1;
+  if (logits_on_host) {
+    const int es = dtype == ALS_F32 ? 4 : 2;
+    ALS_TRY(ensure_stage(ctx, static_cast<size_t>(s.elems()) * es));
+    ALS_TRY(stage_chunk(ctx, static_cast<const unsigned char*>(logits), s, es, 0, B, &b));
+    ALS_CUDA(ctx, cudaStreamWaitEvent(ctx->stream, ctx->ev_copied[b], 0));
+    dev_logits = ctx->stage[b];
+  } else {
+    ALS_TRY(check_device_ptr(ctx, logits, "logits"));
+  }
+  // The index vector rides the compute stream (pageable source: staged by the driver before returning).
+  ALS_CUDA(ctx, cudaMemcpyAsync(ctx->index_dev, example_index, static_cast<size_t>(B) * sizeof(int64_t),
+                                cudaMemcpyHostToDevice, ctx->stream));
+  ALS_TRY(score_device(ctx, dev_logits, dtype, s, measure, nullptr, ctx->pool32, ctx->index_dev, ctx->pool_n, nullptr,
+                       nullptr, nullptr, 0.f, ctx->stream));
+  if (b >= 0) {
+    ALS_CUDA(ctx, cudaEventRecord(ctx->ev_scored[b], ctx->stream));
+    // "returns once staged": the caller may reuse its host buffer after this call
+    ALS_CUDA(ctx, cudaEventSynchronize(ctx->ev_copied[b]));
+  }
+  return ALS_OK;
+}
+
+int als_pool_scores(als_ctx* ctx, float* out, int64_t num_examples) {
+  if (!ctx) return fail(nullptr, ALS_ERR_INVALID, "context is NULL");
+  if (ctx->pool_n < 0) return fail(ctx, ALS_ERR_STATE, "als_pool_begin has not been called");
+  if (num_examples != ctx->pool_n) return fail(ctx, ALS_ERR_INVALID, "num_examples=%lld but the pool holds %lld",
+                                               (long long)num_examples, (long long)ctx->pool_n);
+  if (num_examples == 0) return ALS_OK;
+  if (!out) return fail(ctx, ALS_ERR_INVALID, "out is NULL");
+  DeviceGuard g(ctx->device);
+  ALS_CUDA(ctx, cudaMemcpyAsync(out, ctx->pool32, static_cast<size_t>(num_examples) * sizeof(float),
+                                cudaMemcpyDeviceToHost, ctx->stream));
+  ALS_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+  return ALS_OK;
+}
+
+static int ensure_select(als_ctx* ctx, int64_t M) {
+  if (M <= ctx->sel_cap) return ALS_OK;
+  int64_t cap = ctx->sel_cap > 0 ? ctx->sel_cap : 4096;
+  while (cap < M) cap *= 2;
+  ALS_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+  void** ptrs[] = {(void**)&ctx->sel_ids, (void**)&ctx->sel_keys, (void**)&ctx->sel_tmp_keys, (void**)&ctx->sel_tmp_ids,
+                   (void**)&ctx->sel_out_keys, (void**)&ctx->sel_out_ids};
+  const size_t sizes[] = {8, 4, 4, 8, 4, 8};
+  for (int i = 0; i < 6; ++i) {
+    if (*ptrs[i]) ALS_CUDA(ctx, cudaFree(*ptrs[i]));
+    *ptrs[i] = nullptr;
+  }
+  ctx->sel_cap = 0;
+  for (int i = 0; i < 6; ++i) ALS_CUDA(ctx, cudaMalloc(ptrs[i], static_cast<size_t>(cap) * sizes[i]));
+  ctx->sel_cap = cap;
+  return ALS_OK;
+}
+
+int als_pool_select(als_ctx* ctx, const int64_t* unlabelled, int64_t M, int64_t selection_size, int64_t* out_ids,
+                    float* out_unlabelled_conf, int64_t* out_count) {
+  if (!ctx) return fail(nullptr, ALS_ERR_INVALID, "context is NULL");
+  if (ctx->pool_n < 0) return fail(ctx, ALS_ERR_STATE, "als_pool_begin has not been called");
+  if (M < 0) return fail(ctx, ALS_ERR_INVALID, "M must be >= 0");
+  if (!out_count) return fail(ctx, ALS_ERR_INVALID, "out_count is NULL");
+  *out_count = 0;
+  if (M == 0) return ALS_OK;
+  if (!unlabelled) return fail(ctx, ALS_ERR_INVALID, "unlabelled is NULL");
+  for (int64_t i = 0; i < M; ++i)
+    if (unlabelled[i] < 0 || unlabelled[i] >= ctx->pool_n)
+      return fail(ctx, ALS_ERR_INVALID, "unlabelled[%lld]=%lld out of range [0, %lld)", (long long)i,
+                  (long long)unlabelled[i], (long long)ctx->pool_n);
+  // :707-708  selection_size = min(len(unlabelled), selection_size); negative sizes never reach here (:779)
+  int64_t k = selection_size < 0 ? 0 : (selection_size < M ? selection_size : M);
+  if (k > 0 && !out_ids) return fail(ctx, ALS_ERR_INVALID, "out_ids is NULL");
+  DeviceGuard g(ctx->device);
+  ALS_TRY(ensure_select(ctx, M));
+  ALS_CUDA(ctx, cudaMemcpyAsync(ctx->sel_ids, unlabelled, static_cast<size_t>(M) * sizeof(int64_t), cudaMemcpyHostToDevice,
+                                ctx->stream));
+  ALS_CUDA(ctx, als::launch_gather(ctx->pool32, ctx->sel_ids, M, ctx->sel_keys, ctx->stream));
+  ctx->launches += 1;
+  if (k > 0) {
+    ALS_CUDA(ctx, als::launch_select(ctx->sel_keys, ctx->sel_ids, M, k, ctx->sel_tmp_keys, ctx->sel_tmp_ids,
+                                     ctx->sel_out_keys, ctx->sel_out_ids, ctx->stream));
+    ctx->launches += 2;
+    ALS_CUDA(ctx, cudaMemcpyAsync(out_ids, ctx->sel_out_ids, static_cast<size_t>(k) * sizeof(int64_t),
+                                  cudaMemcpyDeviceToHost, ctx->stream));
+  }
+  if (out_unlabelled_conf)
+    ALS_CUDA(ctx, cudaMemcpyAsync(out_unlabelled_conf, ctx->sel_keys, static_cast<size_t>(M) * sizeof(float),
+                                  cudaMemcpyDeviceToHost, ctx->stream));
+  ALS_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+  *out_count = k;
+  return ALS_OK;
+}
+
+int als_select_smallest(als_ctx* ctx, const float* keys, const int64_t* ids, int64_t M, int64_t k, float* out_keys,
+                        int64_t* out_ids, void* stream) {
+  if (!ctx) return fail(nullptr, ALS_ERR_INVALID, "context is NULL");
+  if (M < 0 || k < 0) return fail(ctx, ALS_ERR_INVALID, "M and k must be >= 0");
+  const int64_t kk = k < M ? k : M;
+  if (kk == 0) return ALS_OK;
+  if (!keys || !ids || !out_keys || !out_ids) return fail(ctx, ALS_ERR_INVALID, "NULL pointer");
+  DeviceGuard g(ctx->device);
+  ALS_TRY(check_device_ptr(ctx, keys, "keys"));
+  ALS_TRY(check_device_ptr(ctx, ids, "ids"));
+  ALS_TRY(check_device_ptr(ctx, out_keys, "out_keys"));
+  ALS_TRY(check_device_ptr(ctx, out_ids, "out_ids"));
+  ALS_TRY(ensure_select(ctx, kk));
+  cudaStream_t st = stream ? static_cast<cudaStream_t>(stream) : ctx->stream;
+  ALS_CUDA(ctx, als::launch_select(keys, reinterpret_cast<const long long*>(ids), M, kk, ctx->sel_tmp_keys,
+                                   ctx->sel_tmp_ids, out_keys, reinterpret_cast<long long*>(out_ids), st));
+  ctx->launches += 2;
+  return ALS_OK;
+}
+
+// ---- synthetic pool / bench helpers ----------------------------------------------------------------
+
+int als_synth_logits(als_ctx* ctx, void* out, int dtype, int64_t T, int64_t n0, int64_t n_imgs, int64_t H, int64_t W,
+                     int64_t C, uint64_t seed, int mc, void* stream) {
+  if (!ctx) return fail(nullptr, ALS_ERR_INVALID, "context is NULL");
+  if (dtype != ALS_F32 && dtype != ALS_BF16) return fail(ctx, ALS_ERR_INVALID, "dtype must be float32 or bfloat16");
+  if (T < 1 || n0 < 0 || n_imgs < 0 || H < 1 || W < 1 || C < 1 || C > 4096)
+    return fail(ctx, ALS_ERR_INVALID, "bad synth shape");
+  if (n_imgs == 0) return ALS_OK;
+  DeviceGuard g(ctx->device);
+  ALS_TRY(check_device_ptr(ctx, out, "out"));
+  if (!out) return fail(ctx, ALS_ERR_INVALID, "out is NULL");
+  cudaStream_t st = stream ? static_cast<cudaStream_t>(stream) : ctx->stream;
+  ALS_CUDA(ctx, als::launch_synth(out, dtype, T, n0, n_imgs, H * W, static_cast<int>(C), seed, mc, st));
+  ctx->launches += 1;
+  return ALS_OK;
+}
+
+int als_flush_l2(als_ctx* ctx, void* stream) {
+  if (!ctx) return fail(nullptr, ALS_ERR_INVALID, "context is NULL");
+  DeviceGuard g(ctx->device);
+  if (!ctx->flush_buf) {
+    ctx->flush_bytes = 512ull << 20;
+    ALS_CUDA(ctx, cudaMalloc(&ctx->flush_buf, ctx->flush_bytes));
+  }
+  cudaStream_t st = stream ? static_cast<cudaStream_t>(stream) : ctx->stream;
+  ALS_CUDA(ctx, als::launch_fill(ctx->flush_buf, ctx->flush_bytes, st));
+  return ALS_OK;
+}
+
+int als_describe_launch(als_ctx* ctx, int dtype, int64_t T, int64_t N, int64_t H, int64_t W, int64_t C, int measure,
+                        char* name, int* grid, int* block, int* smem_bytes, int* stages, int* tile_pixels) {
+  const Shape s{T, N, H, W, C};
+  ALS_TRY(check_common(ctx, reinterpret_cast<const void*>(16), dtype, s, measure, false));
+  DeviceGuard g(ctx->device);
+  const int es = dtype == ALS_F32 ? 4 : 2;
+  const bool aligned = (T == 1) || ((N * s.P() * C * es) % 16 == 0);
+  als::LaunchPlan plan = als::plan_score(dtype, static_cast<int>(C), measure, static_cast<int>(T), N * s.P(), aligned,
+                                         ctx->num_sms, ctx->max_smem);
+  if (name) snprintf(name, 128, "%s dtype=%s C=%lld lanes/pixel=%d pixels/thread=%d", plan.name, dtype == ALS_F32 ? "f32" : "bf16",
+                     (long long)C, plan.lanes_per_pixel, plan.pixels_per_thread);
+  if (grid) *grid = plan.grid;
+  if (block) *block = plan.block;
+  if (smem_bytes) *smem_bytes = plan.smem_bytes;
+  if (stages) *stages = plan.stages;
+  if (tile_pixels) *tile_pixels = plan.tile_pixels;
+  return ALS_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,47 @@
+// Host-visible description of one scoring launch.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace als {
+
+struct ScoreParams {
+  const void* logits;       // [T][N][P][C], class innermost (active_learning.py:231)
+  long long sample_stride;  // elements between MC samples = N*P*C
+  long long total_pixels;   // N*P
+  long long P;              // pixels per image = H*W
+  long long num_tiles;
+  int T;
+  int C;
+  int measure;
+  int stages;
+  float inv_log_c;  // 1 / log(float32(C))        (active_learning.py:248-249)
+  float threshold;  // alparams["threshold"]      (active_learning.py:265)
+  float inv_T;
+  float fx_scale;        // 2^fx_shift: per-pixel confidences are summed in Q(fx_shift) fixed point
+  long long* acc;        // [N] fixed-point per-image sums (zero on entry; finalize re-zeroes)
+  unsigned int* flags;   // [N] bit0: a NaN confidence was seen
+  float* conf_map;       // optional [N*P]
+  uint8_t* label;        // optional [N*P]
+  uint8_t* mask;         // optional [N*P]
+};
+
+struct LaunchPlan {
+  const void* func;   // nullptr -> generic fallback
+  const char* name;
+  int grid, block, smem_bytes, stages, tile_pixels, lanes_per_pixel, pixels_per_thread;
+  bool tiled;
+};
+
+// Chooses the kernel for (dtype, C, measure, T); never fails (falls back to the generic kernel).
+LaunchPlan plan_score(int dtype, int C, int measure, int T, long long total_pixels, bool aligned,
+                      int num_sms, int max_smem_per_block);
+
+cudaError_t launch_score(const LaunchPlan& plan, int dtype, ScoreParams p, cudaStream_t stream);
+
+// scores64[i] = flags ? NaN : acc * 2^-shift / P ; optional f32 scatter; re-zeroes acc/flags.
+cudaError_t launch_finalize(long long* acc, unsigned int* flags, int n, double inv_scale_p,
+                            double* scores64, float* pool32, const long long* example_index, long long num_examples,
+                            cudaStream_t stream);
+
+}  // namespace als
