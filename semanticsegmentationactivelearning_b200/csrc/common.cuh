@@ -83,6 +83,13 @@ __device__ __forceinline__ float rcp_approx(float x) {
   return y;
 }
 
+// max that propagates NaN (fmaxf drops it): keeps a NaN logit visible after the -inf clamp
+__device__ __forceinline__ float max_nan(float a, float b) {
+  float y;
+  asm("max.NaN.f32 %0, %1, %2;" : "=f"(y) : "f"(a), "f"(b));
+  return y;
+}
+
 // xor-shuffle reductions inside groups of G adjacent lanes (G power of two)
 template <int G>
 __device__ __forceinline__ float group_max(float v) {

@@ -180,7 +180,7 @@ __device__ __forceinline__ float conf_single(float (&x)[CL], int nvalid, const S
   for (int j = 0; j < CL; ++j) {
     if (EXACT || j < nvalid) {
       float d = x[j] - m1;
-      if constexpr (MEASURE == kEntropy) d = fmaxf(d, -FLT_MAX);  // -inf logits: p = 0, 0*log(tiny) = 0
+      if constexpr (MEASURE == kEntropy) d = max_nan(d, -FLT_MAX);  // -inf logits: p = 0, 0*log(tiny) = 0
       const float e = ex2_approx(d * kLog2e);
       S += e;
       if constexpr (MEASURE == kEntropy) A = fmaf(e, d, A);
@@ -487,7 +487,7 @@ __global__ void __launch_bounds__(kGenericThreads) score_generic_kernel(const Sc
       }
       float S = 0.f, A = 0.f;
       for (int c = 0; c < C; ++c) {
-        const float d = fmaxf(ld_elem(px + c) - m1, -FLT_MAX);
+        const float d = max_nan(ld_elem(px + c) - m1, -FLT_MAX);
         const float e = ex2_approx(d * kLog2e);
         S += e;
         A = fmaf(e, d, A);
