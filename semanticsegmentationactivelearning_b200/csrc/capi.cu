@@ -44,6 +44,7 @@ struct als_ctx {
   // per-image fixed-point accumulators
   long long* acc = nullptr;
   unsigned int* flags = nullptr;
+  unsigned long long* tile_counter = nullptr;
   int64_t acc_cap = 0;
   // device scratch for scores / indices
   double* scores_dev = nullptr;
@@ -215,11 +216,12 @@ int score_device(als_ctx* ctx, const void* logits, int dtype, const Shape& s, in
   p.fx_scale = ldexpf(1.0f, shift);
   p.acc = ctx->acc;
   p.flags = ctx->flags;
+  p.tile_counter = ctx->tile_counter;
   p.conf_map = conf_map;
   p.label = label;
   p.mask = mask;
   ALS_CUDA(ctx, als::launch_score(plan, dtype, p, stream));
-  ALS_CUDA(ctx, als::launch_finalize(ctx->acc, ctx->flags, static_cast<int>(s.N), ldexp(1.0, -shift) / static_cast<double>(P),
+  ALS_CUDA(ctx, als::launch_finalize(ctx->acc, ctx->flags, ctx->tile_counter, static_cast<int>(s.N), ldexp(1.0, -shift) / static_cast<double>(P),
                                      scores64, pool32, example_index_dev, num_examples, stream));
   ctx->launches += 2;
   return ALS_OK;
@@ -342,6 +344,8 @@ int als_ctx_create(int device, als_ctx** out) {
     ok = cudaEventCreateWithFlags(&ctx->ev_copied[b], cudaEventDisableTiming) == cudaSuccess &&
          cudaEventCreateWithFlags(&ctx->ev_scored[b], cudaEventDisableTiming) == cudaSuccess;
   }
+  ok = ok && cudaMalloc(reinterpret_cast<void**>(&ctx->tile_counter), 128) == cudaSuccess &&
+       cudaMemset(ctx->tile_counter, 0, 128) == cudaSuccess;
   if (!ok) {
     (void)cudaGetLastError();
     als_ctx_destroy(ctx);
@@ -356,7 +360,7 @@ int als_ctx_destroy(als_ctx* ctx) {
   DeviceGuard g(ctx->device);
   if (ctx->stream) cudaStreamSynchronize(ctx->stream);
   if (ctx->copy_stream) cudaStreamSynchronize(ctx->copy_stream);
-  void* ptrs[] = {ctx->acc, ctx->flags, ctx->scores_dev, ctx->index_dev, ctx->pool32, ctx->sel_ids, ctx->sel_keys,
+  void* ptrs[] = {ctx->acc, ctx->flags, ctx->tile_counter, ctx->scores_dev, ctx->index_dev, ctx->pool32, ctx->sel_ids, ctx->sel_keys,
                   ctx->sel_tmp_keys, ctx->sel_tmp_ids, ctx->sel_out_keys, ctx->sel_out_ids, ctx->stage[0], ctx->stage[1],
                   ctx->maps_dev, ctx->flush_buf};
   for (void* p : ptrs)

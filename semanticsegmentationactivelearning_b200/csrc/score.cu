@@ -24,6 +24,8 @@
 namespace als {
 
 enum : int { kEntropy = 0, kMargin = 1, kConfidence = 2, kVariance = 3, kMulti = 4 };
+constexpr int kSmemHeader = 128 + 256;  // mbarriers (2 x 8 x 8 B) + per-stage TileMeta (8 x 24 B, padded)
+static_assert(kSmemHeader % 128 == 0 && kMaxStages * 24 <= 256, "stage buffers must stay 128-byte aligned");
 
 // ---- compile-time launch policy -------------------------------------------------------
 __host__ __device__ constexpr int lpp_for(int C) { return C <= 36 ? 1 : C <= 72 ? 2 : C <= 144 ? 4 : 8; }
@@ -296,6 +298,13 @@ __device__ __forceinline__ void emit_pixel(const ScoreParams& p, ImageAcc& acc, 
 }
 
 // ---- the tiled kernel ------------------------------------------------------------------------
+// Per-stage tile descriptor the producer publishes next to the data (sample 0 of a tile only).
+struct TileMeta {
+  long long pix0;  // first global pixel of the tile, -1 = no more work
+  long long img;   // image of that pixel
+  long long off;   // its offset inside the image
+};
+
 template <typename E, int C, int MEASURE>
 __global__ void __launch_bounds__(kBlockThreads, 2) score_tiles_kernel(const ScoreParams p) {
   constexpr bool MULTI = (MEASURE == kMulti);
@@ -305,7 +314,8 @@ __global__ void __launch_bounds__(kBlockThreads, 2) score_tiles_kernel(const Sco
   extern __shared__ __align__(128) unsigned char smem[];
   uint64_t* full = reinterpret_cast<uint64_t*>(smem);
   uint64_t* empty = full + kMaxStages;
-  unsigned char* stage_base = smem + 128;
+  TileMeta* meta = reinterpret_cast<TileMeta*>(smem + 128);
+  unsigned char* stage_base = smem + kSmemHeader;
   const int nstage = p.stages;
 
   if (threadIdx.x == 0) {
@@ -321,27 +331,49 @@ __global__ void __launch_bounds__(kBlockThreads, 2) score_tiles_kernel(const Sco
   const int lane = threadIdx.x & 31;
 
   if (warp == kConsumerThreads / 32) {
-    // ===== producer: one lane feeds the ring with 1-D bulk copies =====
+    // ===== producer: one lane claims tiles and feeds the ring with 1-D bulk copies =====
+    // Tiles are claimed dynamically (first one static, the rest from a global counter) so SMs that
+    // see less HBM bandwidth simply take fewer tiles; the integer per-image sums make the result
+    // independent of who scored what.
     if (lane == 0) {
       const uint64_t policy = l2_policy_evict_first();
       const E* base = static_cast<const E*>(p.logits);
       int s = 0;
       uint32_t ph = 0;
-      for (long long tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
+      long long tile = blockIdx.x;
+      while (true) {
+        const bool live = tile < p.num_tiles;
+        // claim the next tile now; its latency hides behind this tile's copies
+        const long long next = live ? static_cast<long long>(gridDim.x) +
+                                          static_cast<long long>(atomicAdd(p.tile_counter, 1ull))
+                                    : tile;
+        if (!live) {
+          mbar_wait(&empty[s], ph ^ 1u);
+          meta[s].pix0 = -1;
+          mbar_arrive_expect_tx(&full[s], 0);
+          break;
+        }
         const long long pix0 = tile * K::TILE_PIX;
         const long long rem = p.total_pixels - pix0;
         const uint32_t npix = rem < K::TILE_PIX ? static_cast<uint32_t>(rem) : K::TILE_PIX;
         const uint32_t bytes = npix * C * ES;
         const uint32_t bulk = bytes & ~15u;
+        const long long img = pix0 / p.P;
         for (int t = 0; t < p.T; ++t) {
           mbar_wait(&empty[s], ph ^ 1u);
           unsigned char* dst = stage_base + static_cast<size_t>(s) * K::STAGE_BYTES;
           const unsigned char* src = reinterpret_cast<const unsigned char*>(base + t * p.sample_stride + pix0 * C);
+          if (t == 0) {
+            meta[s].pix0 = pix0;
+            meta[s].img = img;
+            meta[s].off = pix0 - img * p.P;
+          }
           for (uint32_t b = bulk; b < bytes; ++b) dst[b] = src[b];  // < 16 trailing bytes of the whole pool
-          mbar_arrive_expect_tx(&full[s], bulk);
+          mbar_arrive_expect_tx(&full[s], bulk);                    // release: publishes meta + tail bytes
           if (bulk) bulk_g2s(dst, src, bulk, &full[s], policy);
           if (++s == nstage) { s = 0; ph ^= 1u; }
         }
+        tile = next;
       }
     }
     return;
@@ -356,14 +388,14 @@ __global__ void __launch_bounds__(kBlockThreads, 2) score_tiles_kernel(const Sco
   const unsigned int run_off = (pl * C + class0) * ES;
 
   ImageAcc acc;
-  long long tile_pix0 = static_cast<long long>(blockIdx.x) * K::TILE_PIX;
-  long long img = tile_pix0 / p.P;
-  long long off = tile_pix0 - img * p.P;
-  const long long stride = static_cast<long long>(gridDim.x) * K::TILE_PIX;
-
   int s = 0;
   uint32_t ph = 0;
-  for (long long tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
+  while (true) {
+    mbar_wait(&full[s], ph);  // sample 0 of the next tile (or the end marker)
+    const long long tile_pix0 = meta[s].pix0;
+    if (tile_pix0 < 0) break;
+    const long long img = meta[s].img;
+    const long long off = meta[s].off;
     const long long rem = p.total_pixels - tile_pix0;
     const int npix = rem < K::TILE_PIX ? static_cast<int>(rem) : K::TILE_PIX;
     if (img != acc.img) {  // CTA-uniform
@@ -373,7 +405,6 @@ __global__ void __launch_bounds__(kBlockThreads, 2) score_tiles_kernel(const Sco
 
     if constexpr (!MULTI) {
       float x[PPT][CL];
-      mbar_wait(&full[s], ph);
       const unsigned char* st = stage_base + static_cast<size_t>(s) * K::STAGE_BYTES + run_off;
       // Pixel slots past the end of the pool (last tile only) hold stale but in-bounds bytes:
       // they are computed like the rest (no divergence around the shuffles) and dropped at emit.
@@ -406,7 +437,7 @@ __global__ void __launch_bounds__(kBlockThreads, 2) score_tiles_kernel(const Sco
       }
       for (int t = 0; t < p.T; ++t) {
         float x[PPT][CL];
-        mbar_wait(&full[s], ph);
+        if (t > 0) mbar_wait(&full[s], ph);
         const unsigned char* st = stage_base + static_cast<size_t>(s) * K::STAGE_BYTES + run_off;
 #pragma unroll
         for (int k = 0; k < PPT; ++k) {
@@ -429,14 +460,6 @@ __global__ void __launch_bounds__(kBlockThreads, 2) score_tiles_kernel(const Sco
         const float conf = conf_multi<CL, LPP, K::EXACT>(mu[k], m2s[k], nvalid, p);
         if (sub == 0 && l < npix) emit_pixel(p, acc, conf, lbl[k], tile_pix0 + l, off + l);
       }
-    }
-
-    tile_pix0 += stride;
-    off += stride;
-    if (off >= p.P) {
-      const long long q = off / p.P;
-      img += q;
-      off -= q * p.P;
     }
   }
   acc.flush(p);
@@ -550,10 +573,12 @@ __global__ void __launch_bounds__(kGenericThreads) score_generic_kernel(const Sc
 }
 
 // ---- finalize: fixed point -> f64 mean (:261-263), f32 scatter by example index (:700) -------
-__global__ void finalize_kernel(long long* __restrict__ acc, unsigned int* __restrict__ flags, int n, double inv_scale_p,
+__global__ void finalize_kernel(long long* __restrict__ acc, unsigned int* __restrict__ flags,
+                                unsigned long long* __restrict__ tile_counter, int n, double inv_scale_p,
                                 double* __restrict__ scores64, float* __restrict__ pool32,
                                 const long long* __restrict__ example_index, long long num_examples) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i == 0) *tile_counter = 0ull;  // ready for the next scoring launch on this stream
   if (i >= n) return;
   const double s = flags[i] ? __longlong_as_double(0x7ff8000000000000ll) : static_cast<double>(acc[i]) * inv_scale_p;
   acc[i] = 0;
@@ -565,11 +590,12 @@ __global__ void finalize_kernel(long long* __restrict__ acc, unsigned int* __res
   }
 }
 
-cudaError_t launch_finalize(long long* acc, unsigned int* flags, int n, double inv_scale_p, double* scores64,
+cudaError_t launch_finalize(long long* acc, unsigned int* flags, unsigned long long* tile_counter, int n,
+                            double inv_scale_p, double* scores64,
                             float* pool32, const long long* example_index, long long num_examples,
                             cudaStream_t stream) {
   if (n <= 0) return cudaSuccess;
-  finalize_kernel<<<(n + 255) / 256, 256, 0, stream>>>(acc, flags, n, inv_scale_p, scores64, pool32, example_index,
+  finalize_kernel<<<(n + 255) / 256, 256, 0, stream>>>(acc, flags, tile_counter, n, inv_scale_p, scores64, pool32, example_index,
                                                        num_examples);
   return cudaGetLastError();
 }
@@ -620,13 +646,13 @@ LaunchPlan plan_score(int dtype, int C, int measure, int T, long long total_pixe
   }
   if (ok) {
     const int stage_bytes = plan.smem_bytes;
-    const int budget = (max_smem_per_block < 112 * 1024 ? max_smem_per_block : 112 * 1024) - 128;
+    const int budget = (max_smem_per_block < 112 * 1024 ? max_smem_per_block : 112 * 1024) - kSmemHeader;
     int stages = budget / stage_bytes;
     if (stages > kMaxStages) stages = kMaxStages;
     if (stages >= 2) {
       plan.tiled = true;
       plan.stages = stages;
-      plan.smem_bytes = 128 + stages * stage_bytes;
+      plan.smem_bytes = kSmemHeader + stages * stage_bytes;
       plan.block = kBlockThreads;
       const long long tiles = (total_pixels + plan.tile_pixels - 1) / plan.tile_pixels;
       int per_sm = 0;

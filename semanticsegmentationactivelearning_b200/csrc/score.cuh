@@ -21,6 +21,7 @@ struct ScoreParams {
   float fx_scale;        // 2^fx_shift: per-pixel confidences are summed in Q(fx_shift) fixed point
   long long* acc;        // [N] fixed-point per-image sums (zero on entry; finalize re-zeroes)
   unsigned int* flags;   // [N] bit0: a NaN confidence was seen
+  unsigned long long* tile_counter;  // dynamic tile scheduler (zero on entry; finalize re-zeroes)
   float* conf_map;       // optional [N*P]
   uint8_t* label;        // optional [N*P]
   uint8_t* mask;         // optional [N*P]
@@ -40,7 +41,8 @@ LaunchPlan plan_score(int dtype, int C, int measure, int T, long long total_pixe
 cudaError_t launch_score(const LaunchPlan& plan, int dtype, ScoreParams p, cudaStream_t stream);
 
 // scores64[i] = flags ? NaN : acc * 2^-shift / P ; optional f32 scatter; re-zeroes acc/flags.
-cudaError_t launch_finalize(long long* acc, unsigned int* flags, int n, double inv_scale_p,
+cudaError_t launch_finalize(long long* acc, unsigned int* flags, unsigned long long* tile_counter, int n,
+                            double inv_scale_p,
                             double* scores64, float* pool32, const long long* example_index, long long num_examples,
                             cudaStream_t stream);
 
