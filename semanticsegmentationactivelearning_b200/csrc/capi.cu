@@ -210,18 +210,19 @@ int score_device(als_ctx* ctx, const void* logits, int dtype, const Shape& s, in
   p.T = static_cast<int>(s.T);
   p.C = static_cast<int>(s.C);
   p.measure = measure;
-  p.inv_log_c = 1.0f / logf(static_cast<float>(s.C));
+  p.inv_log2_c = static_cast<float>(1.0 / log2(static_cast<double>(s.C)));
   p.threshold = threshold;
   p.inv_T = 1.0f / static_cast<float>(s.T);
   p.fx_scale = ldexpf(1.0f, shift);
   p.acc = ctx->acc;
+  p.acc_stride = ctx->acc_cap;
   p.flags = ctx->flags;
   p.tile_counter = ctx->tile_counter;
   p.conf_map = conf_map;
   p.label = label;
   p.mask = mask;
   ALS_CUDA(ctx, als::launch_score(plan, dtype, p, stream));
-  ALS_CUDA(ctx, als::launch_finalize(ctx->acc, ctx->flags, ctx->tile_counter, static_cast<int>(s.N), ldexp(1.0, -shift) / static_cast<double>(P),
+  ALS_CUDA(ctx, als::launch_finalize(ctx->acc, ctx->acc_cap, ctx->flags, ctx->tile_counter, static_cast<int>(s.N), ldexp(1.0, -shift) / static_cast<double>(P),
                                      scores64, pool32, example_index_dev, num_examples, stream));
   ctx->launches += 2;
   return ALS_OK;
@@ -237,9 +238,9 @@ int ensure_acc(als_ctx* ctx, int64_t n) {
   ctx->acc = nullptr;
   ctx->flags = nullptr;
   ctx->acc_cap = 0;
-  ALS_CUDA(ctx, cudaMalloc(reinterpret_cast<void**>(&ctx->acc), static_cast<size_t>(cap) * sizeof(long long)));
+  ALS_CUDA(ctx, cudaMalloc(reinterpret_cast<void**>(&ctx->acc), static_cast<size_t>(cap) * als::kAccReplicas * sizeof(long long)));
   ALS_CUDA(ctx, cudaMalloc(reinterpret_cast<void**>(&ctx->flags), static_cast<size_t>(cap) * sizeof(unsigned int)));
-  ALS_CUDA(ctx, cudaMemset(ctx->acc, 0, static_cast<size_t>(cap) * sizeof(long long)));
+  ALS_CUDA(ctx, cudaMemset(ctx->acc, 0, static_cast<size_t>(cap) * als::kAccReplicas * sizeof(long long)));
   ALS_CUDA(ctx, cudaMemset(ctx->flags, 0, static_cast<size_t>(cap) * sizeof(unsigned int)));
   ctx->acc_cap = cap;
   return ALS_OK;

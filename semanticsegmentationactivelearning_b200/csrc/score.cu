@@ -18,6 +18,7 @@
 
 #include <cuda_bf16.h>
 #include <float.h>
+#include <stdlib.h>
 
 #include "common.cuh"
 
@@ -58,6 +59,9 @@ struct Cfg {
   static constexpr int STAGE_BYTES = ((TILE_PIX * C * ES + 127) / 128) * 128;
   // widest shared-memory access every lane's run start is aligned to
   static constexpr int VB = EXACT ? pow2_divisor(gcd_i(CL * ES, C * ES), 16) : ES;
+  // resident CTAs per SM the kernel is compiled for: 3 when the per-thread class registers are few
+  // (more warps hide the dependent MUFU/FMA chains), else 2
+  static constexpr int MINB = (PPT * CL <= 24) ? 3 : 2;
   static_assert((LPP - 1) * CL < C, "every lane must own at least one class");
 };
 
@@ -158,13 +162,39 @@ __device__ __forceinline__ int group_argmax(const float (&x)[CL], int nvalid, in
   return bi;
 }
 
-// T == 1: confidence of one pixel straight from its logits (x is overwritten).
+// T == 1: confidence of one pixel straight from its logits.
 //   softmax (:239): e = exp(x - max), p = e / S       -- never materialised
 //   entropy (:243-251): -sum p log p = log S - (sum e*(x-max)) / S   (one log per pixel, not C)
 //   margin  (:254-255): p(1) - p(2) = (1 - exp(x(2) - max)) / S
 //   max-prob (:258):    1 / S
+// Entropy works in log2 units with t = fma(x, log2e, -max*log2e): the rounding of max*log2e
+// shifts every t by the same epsilon, which cancels between log2 S and (sum e*t)/S.  A -inf
+// logit gives e*t = 0*(-inf) = NaN; instead of clamping every class, a NaN result re-runs the
+// pixel's warp with the clamp (CLAMP = true), which also tells a real NaN from that artefact.
+template <int CL, int LPP, bool EXACT, bool CLAMP>
+__device__ __forceinline__ float entropy_conf(const float (&x)[CL], int nvalid, float m1, const ScoreParams& p) {
+  const float ml = m1 * kLog2e;
+  float S = 0.f, A = 0.f;
+#pragma unroll
+  for (int j = 0; j < CL; ++j) {
+    if (EXACT || j < nvalid) {
+      float t = fmaf(x[j], kLog2e, -ml);
+      if constexpr (CLAMP) t = max_nan(t, -FLT_MAX);  // -inf logits: p = 0 and 0*log(tiny) = 0 (:243)
+      const float e = ex2_approx(t);
+      S += e;
+      A = fmaf(e, t, A);
+    }
+  }
+  if constexpr (LPP > 1) {
+    S = group_sum<LPP>(S);
+    A = group_sum<LPP>(A);
+  }
+  const float h2 = fmaf(-A, rcp_approx(S), lg2_approx(S));  // entropy in bits
+  return fmaf(-h2, p.inv_log2_c, 1.0f);                      // 1 - H / log(C)
+}
+
 template <int CL, int LPP, bool EXACT, int MEASURE>
-__device__ __forceinline__ float conf_single(float (&x)[CL], int nvalid, const ScoreParams& p) {
+__device__ __forceinline__ float conf_single(const float (&x)[CL], int nvalid, const ScoreParams& p) {
   float m1 = x[0], m2 = -INFINITY;
 #pragma unroll
   for (int j = 1; j < CL; ++j) {
@@ -177,34 +207,27 @@ __device__ __forceinline__ float conf_single(float (&x)[CL], int nvalid, const S
     if constexpr (MEASURE == kMargin) group_top2<LPP>(m1, m2);
     else m1 = group_max<LPP>(m1);
   }
-  float S = 0.f, A = 0.f;
-#pragma unroll
-  for (int j = 0; j < CL; ++j) {
-    if (EXACT || j < nvalid) {
-      float d = x[j] - m1;
-      if constexpr (MEASURE == kEntropy) d = max_nan(d, -FLT_MAX);  // -inf logits: p = 0, 0*log(tiny) = 0
-      const float e = ex2_approx(d * kLog2e);
-      S += e;
-      if constexpr (MEASURE == kEntropy) A = fmaf(e, d, A);
-    }
-  }
-  if constexpr (LPP > 1) {
-    S = group_sum<LPP>(S);
-    if constexpr (MEASURE == kEntropy) A = group_sum<LPP>(A);
-  }
-  const float r = rcp_approx(S);
   if constexpr (MEASURE == kEntropy) {
-    const float h = fmaf(lg2_approx(S), kLn2, -A * r);
-    return fmaf(-h, p.inv_log_c, 1.0f);
-  } else if constexpr (MEASURE == kMargin) {
-    const float e2 = ex2_approx((m2 - m1) * kLog2e);
-    return (1.0f - e2) * r;
+    float conf = entropy_conf<CL, LPP, EXACT, false>(x, nvalid, m1, p);
+    if (__any_sync(0xffffffffu, !(conf == conf)))  // rare: some pixel of this warp has a -inf / NaN logit
+      conf = entropy_conf<CL, LPP, EXACT, true>(x, nvalid, m1, p);
+    return conf;
   } else {
-    return r;
+    float S = 0.f;
+#pragma unroll
+    for (int j = 0; j < CL; ++j)
+      if (EXACT || j < nvalid) S += ex2_approx((x[j] - m1) * kLog2e);
+    if constexpr (LPP > 1) S = group_sum<LPP>(S);
+    const float r = rcp_approx(S);
+    if constexpr (MEASURE == kMargin) return (1.0f - ex2_approx((m2 - m1) * kLog2e)) * r;
+    else return r;
   }
 }
 
 // T > 1: fold one sample's softmax into the running per-class mean and the summed M2.
+// Welford with delta = p - mu_old:  mu += delta / n,  M2 += delta * (p - mu_new) = delta^2 * (1 - 1/n),
+// so the per-class work is three FFMAs; p = e / S is formed inside the first one.  The exponent
+// argument is one FFMA as well: the shared rounding error of max*log2e cancels in e / S.
 template <int CL, int LPP, bool EXACT>
 __device__ __forceinline__ void welford_update(float (&x)[CL], int nvalid, float inv_t, float (&mu)[CL], float& m2s) {
   float m1 = x[0];
@@ -212,25 +235,27 @@ __device__ __forceinline__ void welford_update(float (&x)[CL], int nvalid, float
   for (int j = 1; j < CL; ++j)
     if (EXACT || j < nvalid) m1 = fmaxf(m1, x[j]);
   if constexpr (LPP > 1) m1 = group_max<LPP>(m1);
+  const float ml = m1 * kLog2e;
   float S = 0.f;
 #pragma unroll
   for (int j = 0; j < CL; ++j) {
     if (EXACT || j < nvalid) {
-      x[j] = ex2_approx((x[j] - m1) * kLog2e);
+      x[j] = ex2_approx(fmaf(x[j], kLog2e, -ml));
       S += x[j];
     }
   }
   if constexpr (LPP > 1) S = group_sum<LPP>(S);
   const float r = rcp_approx(S);
+  float q = 0.f;
 #pragma unroll
   for (int j = 0; j < CL; ++j) {
     if (EXACT || j < nvalid) {
-      const float pj = x[j] * r;
-      const float delta = pj - mu[j];
+      const float delta = fmaf(x[j], r, -mu[j]);
       mu[j] = fmaf(delta, inv_t, mu[j]);
-      m2s = fmaf(delta, pj - mu[j], m2s);
+      q = fmaf(delta, delta, q);
     }
   }
+  m2s = fmaf(q, 1.0f - inv_t, m2s);
 }
 
 // T > 1: measure of the predictive mean (or the summed population variance).
@@ -244,9 +269,9 @@ __device__ __forceinline__ float conf_multi(const float (&mu)[CL], float m2s, in
     float h = 0.f;
 #pragma unroll
     for (int j = 0; j < CL; ++j)
-      if (EXACT || j < nvalid) h = fmaf(-mu[j], lg2_approx(mu[j] + kTiny) * kLn2, h);
+      if (EXACT || j < nvalid) h = fmaf(-mu[j], lg2_approx(mu[j] + kTiny), h);  // bits
     if constexpr (LPP > 1) h = group_sum<LPP>(h);
-    return fmaf(-h, p.inv_log_c, 1.0f);
+    return fmaf(-h, p.inv_log2_c, 1.0f);
   }
   float m1 = mu[0], m2 = -INFINITY;
 #pragma unroll
@@ -263,6 +288,15 @@ __device__ __forceinline__ float conf_multi(const float (&mu)[CL], float m2s, in
 // ---- per-image accumulation ---------------------------------------------------------------
 // f64 mean of the f32 map (:261-263) done as an exact integer sum of round(conf * 2^shift):
 // integer adds commute, so the result is independent of CTA scheduling (run-to-run identical).
+// All CTAs walk the images in step, so every warp flushes to the same image at about the same
+// time; kAccReplicas copies of the accumulator vector (picked by warp and CTA, laid out
+// [replica][acc_stride] so replicas sit in different L2 slices) keep those REDs from serialising
+// on one address.  finalize_kernel adds the replicas up.
+__device__ __forceinline__ long long acc_slot(const ScoreParams& p) {
+  const int replica = ((threadIdx.x >> 5) & 7) | ((blockIdx.x & (kAccReplicas / 8 - 1)) << 3);
+  return static_cast<long long>(replica) * p.acc_stride;
+}
+
 struct ImageAcc {
   long long sum = 0;
   unsigned int nan = 0;
@@ -272,7 +306,7 @@ struct ImageAcc {
     const long long s = warp_sum_ll(sum);
     const unsigned int n = __any_sync(0xffffffffu, nan != 0);
     if ((threadIdx.x & 31) == 0 && img >= 0) {
-      if (s != 0) atomicAdd(reinterpret_cast<unsigned long long*>(p.acc + img), static_cast<unsigned long long>(s));
+      if (s != 0) atomicAdd(reinterpret_cast<unsigned long long*>(p.acc + acc_slot(p) + img), static_cast<unsigned long long>(s));
       if (n) atomicOr(p.flags + img, 1u);
     }
     sum = 0;
@@ -280,16 +314,18 @@ struct ImageAcc {
   }
 };
 
+// l: pixel slot in the tile; in_img: slots below it belong to the tile's first image (acc.img).
 __device__ __forceinline__ void emit_pixel(const ScoreParams& p, ImageAcc& acc, float conf, int lbl,
-                                           long long g, long long rel) {
+                                           long long tile_pix0, long long off, int l, int in_img) {
   const bool isnan_ = !(conf == conf);
   const long long fx = isnan_ ? 0ll : __float2ll_rn(conf * p.fx_scale);
-  if (rel < p.P) {
+  const long long g = tile_pix0 + l;
+  if (l < in_img) {
     acc.sum += fx;
     acc.nan |= isnan_ ? 1u : 0u;
   } else {  // tile straddles an image boundary: rare, go straight to the image's accumulator
-    const long long q = acc.img + rel / p.P;
-    atomicAdd(reinterpret_cast<unsigned long long*>(p.acc + q), static_cast<unsigned long long>(fx));
+    const long long q = acc.img + (off + l) / p.P;
+    atomicAdd(reinterpret_cast<unsigned long long*>(p.acc + acc_slot(p) + q), static_cast<unsigned long long>(fx));
     if (isnan_) atomicOr(p.flags + q, 1u);
   }
   if (p.conf_map) p.conf_map[g] = conf;
@@ -306,7 +342,7 @@ struct TileMeta {
 };
 
 template <typename E, int C, int MEASURE>
-__global__ void __launch_bounds__(kBlockThreads, 2) score_tiles_kernel(const ScoreParams p) {
+__global__ void __launch_bounds__(kBlockThreads, Cfg<E, C, (MEASURE == kMulti)>::MINB) score_tiles_kernel(const ScoreParams p) {
   constexpr bool MULTI = (MEASURE == kMulti);
   using K = Cfg<E, C, MULTI>;
   constexpr int CL = K::CL, LPP = K::LPP, PPT = K::PPT, G = K::G, ES = K::ES;
@@ -398,6 +434,8 @@ __global__ void __launch_bounds__(kBlockThreads, 2) score_tiles_kernel(const Sco
     const long long off = meta[s].off;
     const long long rem = p.total_pixels - tile_pix0;
     const int npix = rem < K::TILE_PIX ? static_cast<int>(rem) : K::TILE_PIX;
+    const long long left = p.P - off;  // pixels of image `img` from the tile start on
+    const int in_img = left < npix ? static_cast<int>(left) : npix;
     if (img != acc.img) {  // CTA-uniform
       acc.flush(p);
       acc.img = img;
@@ -422,7 +460,7 @@ __global__ void __launch_bounds__(kBlockThreads, 2) score_tiles_kernel(const Sco
         int lbl = 0;
         if (p.label) lbl = group_argmax<CL, LPP>(x[k], nvalid, class0);
         const float conf = conf_single<CL, LPP, K::EXACT, MEASURE>(x[k], nvalid, p);
-        if (sub == 0 && l < npix) emit_pixel(p, acc, conf, lbl, tile_pix0 + l, off + l);
+        if (sub == 0 && l < npix) emit_pixel(p, acc, conf, lbl, tile_pix0, off, l, in_img);
       }
     } else {
       float mu[PPT][CL];
@@ -458,7 +496,7 @@ __global__ void __launch_bounds__(kBlockThreads, 2) score_tiles_kernel(const Sco
       for (int k = 0; k < PPT; ++k) {
         const int l = k * G + pl;
         const float conf = conf_multi<CL, LPP, K::EXACT>(mu[k], m2s[k], nvalid, p);
-        if (sub == 0 && l < npix) emit_pixel(p, acc, conf, lbl[k], tile_pix0 + l, off + l);
+        if (sub == 0 && l < npix) emit_pixel(p, acc, conf, lbl[k], tile_pix0, off, l, in_img);
       }
     }
   }
@@ -483,7 +521,7 @@ __global__ void __launch_bounds__(kGenericThreads) score_generic_kernel(const Sc
   unsigned int acc_nan = 0;
   auto flush = [&]() {
     if (acc_img >= 0) {
-      if (acc_sum) atomicAdd(reinterpret_cast<unsigned long long*>(p.acc + acc_img), static_cast<unsigned long long>(acc_sum));
+      if (acc_sum) atomicAdd(reinterpret_cast<unsigned long long*>(p.acc + acc_slot(p) + acc_img), static_cast<unsigned long long>(acc_sum));
       if (acc_nan) atomicOr(p.flags + acc_img, 1u);
     }
     acc_sum = 0;
@@ -516,7 +554,7 @@ __global__ void __launch_bounds__(kGenericThreads) score_generic_kernel(const Sc
         A = fmaf(e, d, A);
       }
       const float r = rcp_approx(S);
-      if (p.measure == kEntropy) conf = fmaf(-fmaf(lg2_approx(S), kLn2, -A * r), p.inv_log_c, 1.0f);
+      if (p.measure == kEntropy) conf = fmaf(-fmaf(lg2_approx(S), kLn2, -A * r), p.inv_log2_c * kLog2e, 1.0f);
       else if (p.measure == kMargin) conf = (1.0f - ex2_approx((m2 - m1) * kLog2e)) * r;
       else conf = r;
     } else {
@@ -544,9 +582,9 @@ __global__ void __launch_bounds__(kGenericThreads) score_generic_kernel(const Sc
         float h = 0.f;
         for (int c = 0; c < C; ++c) {
           const float m = mu_s[c * kGenericThreads + threadIdx.x];
-          h = fmaf(-m, lg2_approx(m + kTiny) * kLn2, h);
+          h = fmaf(-m, lg2_approx(m + kTiny), h);
         }
-        conf = fmaf(-h, p.inv_log_c, 1.0f);
+        conf = fmaf(-h, p.inv_log2_c, 1.0f);
       } else {
         float m1 = mu_s[threadIdx.x], m2 = -INFINITY;
         for (int c = 1; c < C; ++c) {
@@ -573,15 +611,20 @@ __global__ void __launch_bounds__(kGenericThreads) score_generic_kernel(const Sc
 }
 
 // ---- finalize: fixed point -> f64 mean (:261-263), f32 scatter by example index (:700) -------
-__global__ void finalize_kernel(long long* __restrict__ acc, unsigned int* __restrict__ flags,
+__global__ void finalize_kernel(long long* __restrict__ acc, long long acc_stride, unsigned int* __restrict__ flags,
                                 unsigned long long* __restrict__ tile_counter, int n, double inv_scale_p,
                                 double* __restrict__ scores64, float* __restrict__ pool32,
                                 const long long* __restrict__ example_index, long long num_examples) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i == 0) *tile_counter = 0ull;  // ready for the next scoring launch on this stream
   if (i >= n) return;
-  const double s = flags[i] ? __longlong_as_double(0x7ff8000000000000ll) : static_cast<double>(acc[i]) * inv_scale_p;
-  acc[i] = 0;
+  long long total = 0;
+#pragma unroll 8
+  for (int r = 0; r < kAccReplicas; ++r) {
+    total += acc[r * acc_stride + i];
+    acc[r * acc_stride + i] = 0;
+  }
+  const double s = flags[i] ? __longlong_as_double(0x7ff8000000000000ll) : static_cast<double>(total) * inv_scale_p;
   flags[i] = 0;
   if (scores64) scores64[i] = s;
   if (pool32) {
@@ -590,12 +633,12 @@ __global__ void finalize_kernel(long long* __restrict__ acc, unsigned int* __res
   }
 }
 
-cudaError_t launch_finalize(long long* acc, unsigned int* flags, unsigned long long* tile_counter, int n,
-                            double inv_scale_p, double* scores64,
+cudaError_t launch_finalize(long long* acc, long long acc_stride, unsigned int* flags, unsigned long long* tile_counter,
+                            int n, double inv_scale_p, double* scores64,
                             float* pool32, const long long* example_index, long long num_examples,
                             cudaStream_t stream) {
   if (n <= 0) return cudaSuccess;
-  finalize_kernel<<<(n + 255) / 256, 256, 0, stream>>>(acc, flags, tile_counter, n, inv_scale_p, scores64, pool32, example_index,
+  finalize_kernel<<<(n + 255) / 256, 256, 0, stream>>>(acc, acc_stride, flags, tile_counter, n, inv_scale_p, scores64, pool32, example_index,
                                                        num_examples);
   return cudaGetLastError();
 }
@@ -621,10 +664,12 @@ static bool pick(int measure, int T, LaunchPlan& plan) {
     using K = Cfg<E, C, true>;
     plan.tile_pixels = K::TILE_PIX; plan.lanes_per_pixel = K::LPP; plan.pixels_per_thread = K::PPT;
     plan.smem_bytes = K::STAGE_BYTES;  // per stage for now
+    plan.ctas_per_sm = K::MINB;
   } else {
     using K = Cfg<E, C, false>;
     plan.tile_pixels = K::TILE_PIX; plan.lanes_per_pixel = K::LPP; plan.pixels_per_thread = K::PPT;
     plan.smem_bytes = K::STAGE_BYTES;
+    plan.ctas_per_sm = K::MINB;
   }
   return true;
 }
@@ -646,7 +691,11 @@ LaunchPlan plan_score(int dtype, int C, int measure, int T, long long total_pixe
   }
   if (ok) {
     const int stage_bytes = plan.smem_bytes;
-    const int budget = (max_smem_per_block < 112 * 1024 ? max_smem_per_block : 112 * 1024) - kSmemHeader;
+    // shared memory per CTA so that `ctas_per_sm` CTAs fit in the SM's 228 KB (1 KB reserved per CTA)
+    int per_cta = (228 * 1024) / plan.ctas_per_sm - 1024;
+    if (const char* env = getenv("ALS_SMEM_KB")) per_cta = atoi(env) * 1024;  // tuning knob (bench only)
+    if (per_cta > max_smem_per_block) per_cta = max_smem_per_block;
+    const int budget = per_cta - kSmemHeader;
     int stages = budget / stage_bytes;
     if (stages > kMaxStages) stages = kMaxStages;
     if (stages >= 2) {

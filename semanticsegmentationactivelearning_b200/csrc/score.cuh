@@ -5,6 +5,8 @@
 
 namespace als {
 
+constexpr int kAccReplicas = 32;  // copies of the per-image accumulator vector (see score.cu)
+
 struct ScoreParams {
   const void* logits;       // [T][N][P][C], class innermost (active_learning.py:231)
   long long sample_stride;  // elements between MC samples = N*P*C
@@ -15,11 +17,12 @@ struct ScoreParams {
   int C;
   int measure;
   int stages;
-  float inv_log_c;  // 1 / log(float32(C))        (active_learning.py:248-249)
+  float inv_log2_c;  // 1 / log2(C): entropy in bits -> H / log(float32(C))   (active_learning.py:248-249)
   float threshold;  // alparams["threshold"]      (active_learning.py:265)
   float inv_T;
   float fx_scale;        // 2^fx_shift: per-pixel confidences are summed in Q(fx_shift) fixed point
-  long long* acc;        // [N] fixed-point per-image sums (zero on entry; finalize re-zeroes)
+  long long* acc;        // [kAccReplicas][acc_stride] fixed-point per-image sums (zero on entry; finalize re-zeroes)
+  long long acc_stride;  // elements between replicas (>= N)
   unsigned int* flags;   // [N] bit0: a NaN confidence was seen
   unsigned long long* tile_counter;  // dynamic tile scheduler (zero on entry; finalize re-zeroes)
   float* conf_map;       // optional [N*P]
@@ -30,7 +33,7 @@ struct ScoreParams {
 struct LaunchPlan {
   const void* func;   // nullptr -> generic fallback
   const char* name;
-  int grid, block, smem_bytes, stages, tile_pixels, lanes_per_pixel, pixels_per_thread;
+  int grid, block, smem_bytes, stages, tile_pixels, lanes_per_pixel, pixels_per_thread, ctas_per_sm;
   bool tiled;
 };
 
@@ -41,8 +44,8 @@ LaunchPlan plan_score(int dtype, int C, int measure, int T, long long total_pixe
 cudaError_t launch_score(const LaunchPlan& plan, int dtype, ScoreParams p, cudaStream_t stream);
 
 // scores64[i] = flags ? NaN : acc * 2^-shift / P ; optional f32 scatter; re-zeroes acc/flags.
-cudaError_t launch_finalize(long long* acc, unsigned int* flags, unsigned long long* tile_counter, int n,
-                            double inv_scale_p,
+cudaError_t launch_finalize(long long* acc, long long acc_stride, unsigned int* flags, unsigned long long* tile_counter,
+                            int n, double inv_scale_p,
                             double* scores64, float* pool32, const long long* example_index, long long num_examples,
                             cudaStream_t stream);
 
