@@ -63,6 +63,18 @@ def parse_args():
     return ap.parse_args()
 
 
+def load_traffic(workload: str, dtype: str):
+    """DRAM bytes per launch of the dominant kernel from the committed ncu capture (or None)."""
+    try:
+        with open(os.path.join(ROOT, "profiles", "ncu_traffic.json")) as f:
+            t = json.load(f)[workload]
+        if t.get("dtype") != dtype:
+            return None
+        return t["dram_bytes_read"] + t["dram_bytes_write"]
+    except Exception:
+        return None
+
+
 def load_peaks():
     try:
         with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
@@ -370,7 +382,9 @@ def main():
                        "kernel": desc},
             "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches * world),
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                         "traffic": None, "peak_source": peak_src, "kernel": desc["kernel"],
+                         "traffic": load_traffic(args.workload, args.dtype) if not args.pool else None,
+                         "traffic_source": "profiles/ncu_traffic.json (dram__bytes_read+write of one ncu --set full launch)",
+                         "peak_source": peak_src, "kernel": desc["kernel"],
                          "bytes_per_launch": bytes_launch, "avg_launch_ms": avg_ms, "launches_timed": len(full),
                          "kernel_share_of_step": kernel_share, "kernel_burst": burst},
             "cpu_baseline": cpu,

@@ -11,7 +11,7 @@ ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv \
     --log-file $OUT/launches_${WL}_${TAG}.csv $CMD > $OUT/ncu_launches_${WL}_${TAG}.log 2>&1
 echo "launch list exit $?"
 $CMD > /dev/null 2>&1 &&
-ncu --set full --clock-control none --import-source on -k regex:score_tiles -s 4 -c 2 \
+ncu --set full --clock-control none --import-source on -k regex:score_tiles -s 4 -c 1 \
     -f -o $OUT/prof_${WL}_${TAG} $CMD > $OUT/ncu_full_${WL}_${TAG}.log 2>&1
 echo "full capture exit $?"
 ls -la $OUT | tail -12

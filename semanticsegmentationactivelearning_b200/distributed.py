@@ -97,9 +97,15 @@ def rank_confidence_sharded(local_scores: np.ndarray, local_ids: np.ndarray, unl
         dist.all_gather_into_tensor(all_sc, torch.from_numpy(ssc).to(dev), group=group)
     all_id = all_id.cpu().numpy(); all_sc = all_sc.cpu().numpy()
     valid = all_id >= 0
-    # unvisited examples keep 0.0 (:685)
-    conf_by_id = dict(zip(all_id[valid].tolist(), all_sc[valid].tolist()))
-    unlabelled_confidence = np.asarray([conf_by_id.get(int(i), 0.0) for i in unlabelled], dtype=np.float32)
+    vid, vsc = all_id[valid], all_sc[valid]
+    # unlabelled_confidence = confidence[unlabelled] (:705); unvisited examples keep 0.0 (:685)
+    unlabelled_confidence = np.zeros(unlabelled.size, np.float32)
+    if vid.size:
+        o = np.argsort(vid, kind="stable")
+        vid, vsc = vid[o], vsc[o]
+        at = np.clip(np.searchsorted(vid, unlabelled), 0, vid.size - 1)
+        hit = vid[at] == unlabelled
+        unlabelled_confidence[hit] = vsc[at[hit]]
 
     if k == 0:
         return np.zeros(0, np.int64), unlabelled_confidence
