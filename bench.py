@@ -43,6 +43,12 @@ WORKLOADS = {
                  desc="Freiburg Forest 6-class entropy @480x640, pool 4096"),
     "cfg5": dict(N=2250, T=16, H=512, W=1024, C=66, measure="variance", resident=50, chunk=50,
                  desc="Mapillary Vistas 66-class MC-dropout T=16, 18000-image pool sharded 8 ways (2250 per GPU)"),
+    # training-path call site (:229-275): the same pass also writes pseudo_confidence f32, pseudo_label u8 and
+    # pseudo_mask u8 (+6 B/pixel of writes); batches of 8 like params["batch_size"], and of 64
+    "train8": dict(N=512, T=1, H=512, W=1024, C=19, measure="entropy", resident=512, chunk=8, maps=True,
+                   desc="PseudoAnnotation scope with per-pixel outputs (conf+label+mask), batches of 8 @512x1024, C=19"),
+    "train64": dict(N=512, T=1, H=512, W=1024, C=19, measure="entropy", resident=512, chunk=64, maps=True,
+                    desc="PseudoAnnotation scope with per-pixel outputs (conf+label+mask), batches of 64 @512x1024, C=19"),
 }
 K_SELECT = 50          # conf/enet_cityscapes_active_learning.json:59
 SEED = 20191013
@@ -253,6 +259,9 @@ def main():
     unl_global = np.arange(world * N, dtype=np.int64)
 
     ev_pairs = []
+    maps = bool(w.get("maps"))
+    out_bytes_pix = 6 if maps else 0
+    map_outs = {}
 
     def step(record: bool):
         sc.pool_begin(N)
@@ -261,7 +270,10 @@ def main():
             if record:
                 e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
                 e0.record()
-            sc.pool_score_batch(buf, idx, measure)
+            if maps:
+                map_outs[nb] = sc.pseudo_annotation(buf if T > 1 else buf[0], measure, 0.9, out=map_outs.get(nb))
+            else:
+                sc.pool_score_batch(buf, idx, measure)
             if record:
                 e1.record()
                 ev_pairs.append((e0, e1, nb))
@@ -304,7 +316,7 @@ def main():
     # dominant kernel: score_tiles_kernel, one launch per chunk (the 2 us finalize launch rides along)
     full = [(a.elapsed_time(b), nb) for a, b, nb in ev_pairs if nb == chunk] or [(a.elapsed_time(b), nb) for a, b, nb in ev_pairs]
     avg_ms = sum(m for m, _ in full) / len(full)
-    bytes_launch = full[0][1] * T * P * C * es
+    bytes_launch = full[0][1] * P * (T * C * es + out_bytes_pix)
     peak, peak_src = load_peaks()
     achieved = bytes_launch / (avg_ms * 1e-3) / 1e9
     kernel_share = sum(a.elapsed_time(b) for a, b, _ in ev_pairs) / ms_total
@@ -325,11 +337,12 @@ def main():
     torch.cuda.synchronize()
     burst_ms = b0.elapsed_time(b1) / n_burst
     burst = {"launches": n_burst, "avg_ms": burst_ms, "GBps": chunks[0][2] * T * P * C * es / (burst_ms * 1e-3) / 1e9,
+             "outputs": "scores only",
              "note": "score+finalize launched back to back on one resident chunk, outside the timed region"}
 
     # ---- e2e: the public API with HOST (pinned) logits, H2D inside the timed region ----------------
     e2e = None
-    if not args.no_e2e:
+    if not args.no_e2e and not maps:
         from semanticsegmentationactivelearning_b200 import rank_confidence
         per_img = T * P * C * es
         bsz = max(1, min(8, int((2 << 30) // per_img)))              # images per sess.run-like batch (<= 8, :689)
@@ -377,7 +390,9 @@ def main():
             "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": ms_step, "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": args.dtype, "data": "synthetic",
             "config": {"workload": args.workload + ": " + w["desc"], "pool_images_per_gpu": N, "T": T, "H": H, "W": W,
-                       "C": C, "measure": measure, "k": K_SELECT, "resident_images": resident, "chunk_images": chunk,
+                       "C": C, "measure": measure, "k": K_SELECT,
+                       "outputs": "scores + pseudo_confidence f32 + pseudo_label u8 + pseudo_mask u8" if maps else "scores",
+                       "resident_images": resident, "chunk_images": chunk,
                        "l2": "inputs larger than L2 (resident set %.1f GB, aliased over the pool)" % (resident * T * P * C * es / 1e9),
                        "kernel": desc},
             "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches * world),

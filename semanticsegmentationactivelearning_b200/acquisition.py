@@ -152,10 +152,12 @@ class Scorer:
         return out
 
     def pseudo_annotation(self, logits, measure: str = "entropy", threshold: float = 0.9, *,
-                          dtype: Optional[str] = None, want_label: bool = True, want_mask: bool = True):
+                          dtype: Optional[str] = None, want_label: bool = True, want_mask: bool = True,
+                          out: Optional[dict] = None):
         """The whole PseudoAnnotation scope in one pass: returns a dict with
         pseudo_confidence f32[N,H,W], pseudo_mean_confidence f64[N], pseudo_label u8[N,H,W],
-        pseudo_mask u8[N,H,W] (conf < threshold ? 0 : 1)."""
+        pseudo_mask u8[N,H,W] (conf < threshold ? 0 : 1).  `out` (device logits only) is a dict
+        returned by an earlier call with the same shape: its tensors are overwritten in place."""
         m = measure_id(measure)
         lg = _Logits(logits, dtype)
         shp = (lg.N, lg.H, lg.W)
@@ -170,10 +172,16 @@ class Scorer:
         else:
             torch = _torch()
             dev = logits.device
-            conf = torch.empty(shp, dtype=torch.float32, device=dev)
-            label = torch.empty(shp, dtype=torch.uint8, device=dev) if want_label else None
-            mask = torch.empty(shp, dtype=torch.uint8, device=dev) if want_mask else None
-            scores = torch.empty(lg.N, dtype=torch.float64, device=dev)
+            if out is not None:
+                conf, scores = out["pseudo_confidence"], out["pseudo_mean_confidence"]
+                label, mask = out["pseudo_label"], out["pseudo_mask"]
+                if tuple(conf.shape) != shp or (want_label and label is None) or (want_mask and mask is None):
+                    raise ValueError("`out` does not match this call (shape %s)" % (shp,))
+            else:
+                conf = torch.empty(shp, dtype=torch.float32, device=dev)
+                label = torch.empty(shp, dtype=torch.uint8, device=dev) if want_label else None
+                mask = torch.empty(shp, dtype=torch.uint8, device=dev) if want_mask else None
+                scores = torch.empty(lg.N, dtype=torch.float64, device=dev)
             stream = torch.cuda.current_stream(dev).cuda_stream
             self._check(self._lib.als_score(
                 self._ctx, lg.ptr, lg.dtype, lg.T, lg.N, lg.H, lg.W, lg.C, m, scores.data_ptr(), conf.data_ptr(),
