@@ -1,11 +1,13 @@
 #!/bin/bash
 # Profiling recipe (B200_PROFILING.md): launch list + one full capture of the dominant kernel.
-# Usage (under gpurun): bash profiles/run_ncu.sh <workload> <tag>
+# Usage (under gpurun): bash profiles/run_ncu.sh <workload> <tag> [extra bench args, e.g. --dtype bf16]
 set -u
 WL=${1:-cfg2}
 TAG=${2:-r01}
+shift; shift
+EXTRA="$*"
 OUT=gpurun_out
-CMD="python bench.py --workload $WL --steps 2 --warmup 3 --no-cpu-baseline --no-e2e"
+CMD="python bench.py --workload $WL --steps 2 --warmup 3 --no-cpu-baseline --no-e2e $EXTRA"
 $CMD > $OUT/plain_${WL}_${TAG}.json 2> $OUT/plain_${WL}_${TAG}.err &&
 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv \
     --log-file $OUT/launches_${WL}_${TAG}.csv $CMD > $OUT/ncu_launches_${WL}_${TAG}.log 2>&1

@@ -83,6 +83,32 @@ __device__ __forceinline__ float rcp_approx(float x) {
   return y;
 }
 
+// ---- packed fp32 pairs (sm_100a: FFMA2 / FADD2 / FMUL2, two fp32 lanes per issue slot) ---------
+typedef unsigned long long f32x2;
+__device__ __forceinline__ f32x2 pack2(float lo, float hi) {
+  f32x2 r;
+  asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi));
+  return r;
+}
+__device__ __forceinline__ void unpack2(f32x2 v, float& lo, float& hi) {
+  asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(v));
+}
+__device__ __forceinline__ f32x2 fma2(f32x2 a, f32x2 b, f32x2 c) {
+  f32x2 d;
+  asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(d) : "l"(a), "l"(b), "l"(c));
+  return d;
+}
+__device__ __forceinline__ f32x2 add2(f32x2 a, f32x2 b) {
+  f32x2 d;
+  asm("add.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b));
+  return d;
+}
+__device__ __forceinline__ float hsum2(f32x2 v) {
+  float lo, hi;
+  unpack2(v, lo, hi);
+  return lo + hi;
+}
+
 // max that propagates NaN (fmaxf drops it): keeps a NaN logit visible after the -inf clamp
 __device__ __forceinline__ float max_nan(float a, float b) {
   float y;

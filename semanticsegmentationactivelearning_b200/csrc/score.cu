@@ -175,14 +175,37 @@ template <int CL, int LPP, bool EXACT, bool CLAMP>
 __device__ __forceinline__ float entropy_conf(const float (&x)[CL], int nvalid, float m1, const ScoreParams& p) {
   const float ml = m1 * kLog2e;
   float S = 0.f, A = 0.f;
+  if constexpr (EXACT && !CLAMP) {
+    // two classes per issue slot: t = x*log2e - ml (FFMA2), S += e (FADD2), A += e*t (FFMA2)
+    const f32x2 l2 = pack2(kLog2e, kLog2e), nml2 = pack2(-ml, -ml);
+    f32x2 S2 = pack2(0.f, 0.f), A2 = pack2(0.f, 0.f);
 #pragma unroll
-  for (int j = 0; j < CL; ++j) {
-    if (EXACT || j < nvalid) {
-      float t = fmaf(x[j], kLog2e, -ml);
-      if constexpr (CLAMP) t = max_nan(t, -FLT_MAX);  // -inf logits: p = 0 and 0*log(tiny) = 0 (:243)
+    for (int j = 0; j + 1 < CL; j += 2) {
+      const f32x2 t2 = fma2(pack2(x[j], x[j + 1]), l2, nml2);
+      float t0, t1;
+      unpack2(t2, t0, t1);
+      const f32x2 e2 = pack2(ex2_approx(t0), ex2_approx(t1));
+      S2 = add2(S2, e2);
+      A2 = fma2(e2, t2, A2);
+    }
+    S = hsum2(S2);
+    A = hsum2(A2);
+    if constexpr (CL & 1) {
+      const float t = fmaf(x[CL - 1], kLog2e, -ml);
       const float e = ex2_approx(t);
       S += e;
       A = fmaf(e, t, A);
+    }
+  } else {
+#pragma unroll
+    for (int j = 0; j < CL; ++j) {
+      if (EXACT || j < nvalid) {
+        float t = fmaf(x[j], kLog2e, -ml);
+        if constexpr (CLAMP) t = max_nan(t, -FLT_MAX);  // -inf logits: p = 0 and 0*log(tiny) = 0 (:243)
+        const float e = ex2_approx(t);
+        S += e;
+        A = fmaf(e, t, A);
+      }
     }
   }
   if constexpr (LPP > 1) {
@@ -191,6 +214,30 @@ __device__ __forceinline__ float entropy_conf(const float (&x)[CL], int nvalid, 
   }
   const float h2 = fmaf(-A, rcp_approx(S), lg2_approx(S));  // entropy in bits
   return fmaf(-h2, p.inv_log2_c, 1.0f);                      // 1 - H / log(C)
+}
+
+// sum_c exp2(x_c*log2e - m1*log2e), two classes per issue slot
+template <int CL, bool EXACT>
+__device__ __forceinline__ float exp_sum(const float (&x)[CL], int nvalid, float m1) {
+  const float ml = m1 * kLog2e;
+  float S = 0.f;
+  if constexpr (EXACT) {
+    const f32x2 l2 = pack2(kLog2e, kLog2e), nml2 = pack2(-ml, -ml);
+    f32x2 S2 = pack2(0.f, 0.f);
+#pragma unroll
+    for (int j = 0; j + 1 < CL; j += 2) {
+      float t0, t1;
+      unpack2(fma2(pack2(x[j], x[j + 1]), l2, nml2), t0, t1);
+      S2 = add2(S2, pack2(ex2_approx(t0), ex2_approx(t1)));
+    }
+    S = hsum2(S2);
+    if constexpr (CL & 1) S += ex2_approx(fmaf(x[CL - 1], kLog2e, -ml));
+  } else {
+#pragma unroll
+    for (int j = 0; j < CL; ++j)
+      if (j < nvalid) S += ex2_approx(fmaf(x[j], kLog2e, -ml));
+  }
+  return S;
 }
 
 template <int CL, int LPP, bool EXACT, int MEASURE>
@@ -213,14 +260,15 @@ __device__ __forceinline__ float conf_single(const float (&x)[CL], int nvalid, c
       conf = entropy_conf<CL, LPP, EXACT, true>(x, nvalid, m1, p);
     return conf;
   } else {
-    float S = 0.f;
-#pragma unroll
-    for (int j = 0; j < CL; ++j)
-      if (EXACT || j < nvalid) S += ex2_approx((x[j] - m1) * kLog2e);
+    float S = exp_sum<CL, EXACT>(x, nvalid, m1);
     if constexpr (LPP > 1) S = group_sum<LPP>(S);
+    // the rounding of m1*log2e shifts every exponent by the same epsilon: take the top terms through the
+    // same expression so it cancels in e / S
+    const float ml = m1 * kLog2e;
     const float r = rcp_approx(S);
-    if constexpr (MEASURE == kMargin) return (1.0f - ex2_approx((m2 - m1) * kLog2e)) * r;
-    else return r;
+    const float e1 = ex2_approx(fmaf(m1, kLog2e, -ml));
+    if constexpr (MEASURE == kMargin) return (e1 - ex2_approx(fmaf(m2, kLog2e, -ml))) * r;
+    else return e1 * r;
   }
 }
 
@@ -229,30 +277,67 @@ __device__ __forceinline__ float conf_single(const float (&x)[CL], int nvalid, c
 // so the per-class work is three FFMAs; p = e / S is formed inside the first one.  The exponent
 // argument is one FFMA as well: the shared rounding error of max*log2e cancels in e / S.
 template <int CL, int LPP, bool EXACT>
-__device__ __forceinline__ void welford_update(float (&x)[CL], int nvalid, float inv_t, float (&mu)[CL], float& m2s) {
+__device__ __forceinline__ void welford_update(float (&x)[CL], int nvalid, float inv_t, float (&nmu)[CL], float& m2s) {
+  // nmu holds the NEGATED running mean so that delta = e*r - mu is a single (packed) FMA
   float m1 = x[0];
 #pragma unroll
   for (int j = 1; j < CL; ++j)
     if (EXACT || j < nvalid) m1 = fmaxf(m1, x[j]);
   if constexpr (LPP > 1) m1 = group_max<LPP>(m1);
   const float ml = m1 * kLog2e;
-  float S = 0.f;
+  float S = 0.f, q = 0.f;
+  if constexpr (EXACT) {
+    const f32x2 l2 = pack2(kLog2e, kLog2e), nml2 = pack2(-ml, -ml);
+    f32x2 e2[CL / 2];
+    f32x2 S2 = pack2(0.f, 0.f);
 #pragma unroll
-  for (int j = 0; j < CL; ++j) {
-    if (EXACT || j < nvalid) {
-      x[j] = ex2_approx(fmaf(x[j], kLog2e, -ml));
-      S += x[j];
+    for (int j = 0; j + 1 < CL; j += 2) {
+      float t0, t1;
+      unpack2(fma2(pack2(x[j], x[j + 1]), l2, nml2), t0, t1);
+      e2[j / 2] = pack2(ex2_approx(t0), ex2_approx(t1));
+      S2 = add2(S2, e2[j / 2]);
     }
-  }
-  if constexpr (LPP > 1) S = group_sum<LPP>(S);
-  const float r = rcp_approx(S);
-  float q = 0.f;
+    S = hsum2(S2);
+    float elast = 0.f;
+    if constexpr (CL & 1) {
+      elast = ex2_approx(fmaf(x[CL - 1], kLog2e, -ml));
+      S += elast;
+    }
+    if constexpr (LPP > 1) S = group_sum<LPP>(S);
+    const float r = rcp_approx(S);
+    const f32x2 r2 = pack2(r, r), nit2 = pack2(-inv_t, -inv_t);
+    f32x2 q2 = pack2(0.f, 0.f);
 #pragma unroll
-  for (int j = 0; j < CL; ++j) {
-    if (EXACT || j < nvalid) {
-      const float delta = fmaf(x[j], r, -mu[j]);
-      mu[j] = fmaf(delta, inv_t, mu[j]);
+    for (int j = 0; j + 1 < CL; j += 2) {
+      f32x2 n2 = pack2(nmu[j], nmu[j + 1]);
+      const f32x2 d2 = fma2(e2[j / 2], r2, n2);  // delta = p - mu
+      n2 = fma2(d2, nit2, n2);                  // -mu -= delta / n
+      q2 = fma2(d2, d2, q2);
+      unpack2(n2, nmu[j], nmu[j + 1]);
+    }
+    q = hsum2(q2);
+    if constexpr (CL & 1) {
+      const float delta = fmaf(elast, r, nmu[CL - 1]);
+      nmu[CL - 1] = fmaf(delta, -inv_t, nmu[CL - 1]);
       q = fmaf(delta, delta, q);
+    }
+  } else {
+#pragma unroll
+    for (int j = 0; j < CL; ++j) {
+      if (j < nvalid) {
+        x[j] = ex2_approx(fmaf(x[j], kLog2e, -ml));
+        S += x[j];
+      }
+    }
+    if constexpr (LPP > 1) S = group_sum<LPP>(S);
+    const float r = rcp_approx(S);
+#pragma unroll
+    for (int j = 0; j < CL; ++j) {
+      if (j < nvalid) {
+        const float delta = fmaf(x[j], r, nmu[j]);
+        nmu[j] = fmaf(delta, -inv_t, nmu[j]);
+        q = fmaf(delta, delta, q);
+      }
     }
   }
   m2s = fmaf(q, 1.0f - inv_t, m2s);
@@ -260,7 +345,7 @@ __device__ __forceinline__ void welford_update(float (&x)[CL], int nvalid, float
 
 // T > 1: measure of the predictive mean (or the summed population variance).
 template <int CL, int LPP, bool EXACT>
-__device__ __forceinline__ float conf_multi(const float (&mu)[CL], float m2s, int nvalid, const ScoreParams& p) {
+__device__ __forceinline__ float conf_multi(const float (&nmu)[CL], float m2s, int nvalid, const ScoreParams& p) {
   if (p.measure == kVariance) {
     if constexpr (LPP > 1) m2s = group_sum<LPP>(m2s);
     return fmaf(-m2s, p.inv_T, 1.0f);
@@ -269,16 +354,16 @@ __device__ __forceinline__ float conf_multi(const float (&mu)[CL], float m2s, in
     float h = 0.f;
 #pragma unroll
     for (int j = 0; j < CL; ++j)
-      if (EXACT || j < nvalid) h = fmaf(-mu[j], lg2_approx(mu[j] + kTiny), h);  // bits
+      if (EXACT || j < nvalid) h = fmaf(nmu[j], lg2_approx(kTiny - nmu[j]), h);  // -sum mu*log2(mu + tiny), bits
     if constexpr (LPP > 1) h = group_sum<LPP>(h);
     return fmaf(-h, p.inv_log2_c, 1.0f);
   }
-  float m1 = mu[0], m2 = -INFINITY;
+  float m1 = -nmu[0], m2 = -INFINITY;
 #pragma unroll
   for (int j = 1; j < CL; ++j) {
     if (EXACT || j < nvalid) {
-      m2 = fmaxf(m2, fminf(m1, mu[j]));
-      m1 = fmaxf(m1, mu[j]);
+      m2 = fmaxf(m2, fminf(m1, -nmu[j]));
+      m1 = fmaxf(m1, -nmu[j]);
     }
   }
   if constexpr (LPP > 1) group_top2<LPP>(m1, m2);
