@@ -250,3 +250,50 @@ def rank_confidence(logits: np.ndarray, unlabelled, selection_size: int, measure
 
     confidence = scatter_scores(num_examples, _batches())
     return select_lowest(confidence, np.asarray(unlabelled), selection_size)
+
+
+# --------------------------------------------------------------------------- #
+# Logits producer: ENet `Final` (models/enet/enet_modules.py:1294-1381)       #
+# --------------------------------------------------------------------------- #
+def conv2d_transpose_same(value: np.ndarray, kernel: np.ndarray, strides=(2, 2), dtype=np.float32) -> np.ndarray:
+    """tf.nn.conv2d_transpose(value, kernel, output_shape=[B, s*h, s*w, C], strides=[1,s,s,1], padding="SAME")
+    -- the only op of ``Final.call`` (models/enet/enet_modules.py:1376-1380).
+
+    value  [B, h, w, Cin]; kernel [kh, kw, Cout, Cin] (TF's conv2d_transpose filter layout, :1341).
+    Defined as the gradient of conv2d w.r.t. its input: the forward conv with SAME padding reads
+    X[s*i + ky - pad_top, s*j + kx - pad_left]; for an even output size 2h, stride 2 and a 3x3 kernel
+    the total padding is 1 and TF puts it at the bottom/right (pad_top = pad_left = 0)
+    [TF-upstream: GetWindowedOutputSize, pad_before = pad_total // 2].  Hence
+        out[s*i + ky - pad_top, s*j + kx - pad_left, c] += sum_o value[i, j, o] * kernel[ky, kx, c, o].
+    One fp32 matmul per tap, accumulated in tap order (TF's own summation order is unspecified)."""
+    v = np.asarray(value, dtype=dtype)
+    k = np.asarray(kernel, dtype=dtype)
+    B, h, w, cin = v.shape
+    kh, kw, cout, cin2 = k.shape
+    assert cin == cin2, "kernel must be [kh, kw, out_channels, in_channels]"
+    sy, sx = strides
+    H, W = sy * h, sx * w
+    pad_y = max((h - 1) * sy + kh - H, 0)
+    pad_x = max((w - 1) * sx + kw - W, 0)
+    top, left = pad_y // 2, pad_x // 2
+    full = np.zeros((B, (h - 1) * sy + kh, (w - 1) * sx + kw, cout), dtype=dtype)
+    for ky in range(kh):
+        for kx in range(kw):
+            contrib = (v.reshape(-1, cin) @ k[ky, kx].T).reshape(B, h, w, cout).astype(dtype)
+            full[:, ky:ky + (h - 1) * sy + 1:sy, kx:kx + (w - 1) * sx + 1:sx, :] += contrib
+    return np.ascontiguousarray(full[:, top:top + H, left:left + W, :])
+
+
+def final_head(features: np.ndarray, kernel: np.ndarray) -> np.ndarray:
+    """``Final.call`` (models/enet/enet_modules.py:1359-1381): [B,h,w,16] -> logits [B,2h,2w,C], fp32."""
+    return conv2d_transpose_same(features, kernel, (2, 2), np.float32)
+
+
+def score_pool_from_features(features: np.ndarray, kernel: np.ndarray, measure: str, flavour: str = "gpu") -> np.ndarray:
+    """Final head + scoring: features [N,h,w,16] or [T,N,h,w,16] -> per-image f64 scores [N]."""
+    f = np.asarray(features, np.float32)
+    if f.ndim == 5:
+        logits = np.stack([final_head(f[t], kernel) for t in range(f.shape[0])], axis=0)
+    else:
+        logits = final_head(f, kernel)
+    return score_pool(logits, measure, flavour)

@@ -25,8 +25,8 @@
 namespace als {
 
 enum : int { kEntropy = 0, kMargin = 1, kConfidence = 2, kVariance = 3, kMulti = 4 };
-constexpr int kSmemHeader = 128 + 256;  // mbarriers (2 x 8 x 8 B) + per-stage TileMeta (8 x 24 B, padded)
-static_assert(kSmemHeader % 128 == 0 && kMaxStages * 24 <= 256, "stage buffers must stay 128-byte aligned");
+constexpr int kSmemHeader = 128 + 256;  // mbarriers (2 x 8 x 8 B) + per-stage TileMeta (8 x 32 B)
+static_assert(kSmemHeader % 128 == 0 && kMaxStages * 32 <= 256, "stage buffers must stay 128-byte aligned");
 
 // ---- compile-time launch policy -------------------------------------------------------
 __host__ __device__ constexpr int lpp_for(int C) { return C <= 36 ? 1 : C <= 72 ? 2 : C <= 144 ? 4 : 8; }
@@ -240,7 +240,9 @@ __device__ __forceinline__ float exp_sum(const float (&x)[CL], int nvalid, float
   return S;
 }
 
-template <int CL, int LPP, bool EXACT, int MEASURE>
+// CLAMP (entropy only): the slower variant that survives -inf logits; the caller re-runs a whole warp
+// with it when the fast variant produced a NaN (once per tile, not per pixel).
+template <int CL, int LPP, bool EXACT, int MEASURE, bool CLAMP = false>
 __device__ __forceinline__ float conf_single(const float (&x)[CL], int nvalid, const ScoreParams& p) {
   float m1 = x[0], m2 = -INFINITY;
 #pragma unroll
@@ -255,10 +257,8 @@ __device__ __forceinline__ float conf_single(const float (&x)[CL], int nvalid, c
     else m1 = group_max<LPP>(m1);
   }
   if constexpr (MEASURE == kEntropy) {
-    float conf = entropy_conf<CL, LPP, EXACT, false>(x, nvalid, m1, p);
-    if (__any_sync(0xffffffffu, !(conf == conf)))  // rare: some pixel of this warp has a -inf / NaN logit
-      conf = entropy_conf<CL, LPP, EXACT, true>(x, nvalid, m1, p);
-    return conf;
+    if constexpr (CLAMP) return entropy_conf<CL, LPP, EXACT, true>(x, nvalid, m1, p);
+    else return entropy_conf<CL, LPP, EXACT, false>(x, nvalid, m1, p);
   } else {
     float S = exp_sum<CL, EXACT>(x, nvalid, m1);
     if constexpr (LPP > 1) S = group_sum<LPP>(S);
@@ -387,6 +387,12 @@ struct ImageAcc {
   unsigned int nan = 0;
   long long img = -1;
 
+  // a pixel known to belong to image `img`; cvt.rni.s64.f32 turns NaN into 0, the flag records it
+  __device__ __forceinline__ void add(float conf, float fx_scale) {
+    nan |= (conf != conf) ? 1u : 0u;
+    sum += __float2ll_rn(conf * fx_scale);
+  }
+
   __device__ __forceinline__ void flush(const ScoreParams& p) {  // warp-collective
     const long long s = warp_sum_ll(sum);
     const unsigned int n = __any_sync(0xffffffffu, nan != 0);
@@ -424,6 +430,8 @@ struct TileMeta {
   long long pix0;  // first global pixel of the tile, -1 = no more work
   long long img;   // image of that pixel
   long long off;   // its offset inside the image
+  int npix;        // pixels in the tile (< TILE_PIX only for the last tile of the pool)
+  int in_img;      // how many of them belong to `img` (the rest start the next image(s))
 };
 
 template <typename E, int C, int MEASURE>
@@ -485,9 +493,13 @@ __global__ void __launch_bounds__(kBlockThreads, Cfg<E, C, (MEASURE == kMulti)>:
           unsigned char* dst = stage_base + static_cast<size_t>(s) * K::STAGE_BYTES;
           const unsigned char* src = reinterpret_cast<const unsigned char*>(base + t * p.sample_stride + pix0 * C);
           if (t == 0) {
+            const long long off = pix0 - img * p.P;
+            const long long left = p.P - off;  // pixels of image `img` from the tile start on
             meta[s].pix0 = pix0;
             meta[s].img = img;
-            meta[s].off = pix0 - img * p.P;
+            meta[s].off = off;
+            meta[s].npix = static_cast<int>(npix);
+            meta[s].in_img = left < npix ? static_cast<int>(left) : static_cast<int>(npix);
           }
           for (uint32_t b = bulk; b < bytes; ++b) dst[b] = src[b];  // < 16 trailing bytes of the whole pool
           mbar_arrive_expect_tx(&full[s], bulk);                    // release: publishes meta + tail bytes
@@ -517,10 +529,10 @@ __global__ void __launch_bounds__(kBlockThreads, Cfg<E, C, (MEASURE == kMulti)>:
     if (tile_pix0 < 0) break;
     const long long img = meta[s].img;
     const long long off = meta[s].off;
-    const long long rem = p.total_pixels - tile_pix0;
-    const int npix = rem < K::TILE_PIX ? static_cast<int>(rem) : K::TILE_PIX;
-    const long long left = p.P - off;  // pixels of image `img` from the tile start on
-    const int in_img = left < npix ? static_cast<int>(left) : npix;
+    const int npix = meta[s].npix;
+    const int in_img = meta[s].in_img;
+    // common case: a full tile inside one image and no per-pixel outputs -> plain per-thread sums
+    const bool plain = (in_img == K::TILE_PIX) && !p.any_out;
     if (img != acc.img) {  // CTA-uniform
       acc.flush(p);
       acc.img = img;
@@ -539,13 +551,32 @@ __global__ void __launch_bounds__(kBlockThreads, Cfg<E, C, (MEASURE == kMulti)>:
       __syncwarp();
       if (lane == 0) mbar_arrive(&empty[s]);  // values are in registers: hand the stage back
       if (++s == nstage) { s = 0; ph ^= 1u; }
+      float conf[PPT];
+      bool bad = false;
 #pragma unroll
       for (int k = 0; k < PPT; ++k) {
-        const int l = k * G + pl;
-        int lbl = 0;
-        if (p.label) lbl = group_argmax<CL, LPP>(x[k], nvalid, class0);
-        const float conf = conf_single<CL, LPP, K::EXACT, MEASURE>(x[k], nvalid, p);
-        if (sub == 0 && l < npix) emit_pixel(p, acc, conf, lbl, tile_pix0, off, l, in_img);
+        conf[k] = conf_single<CL, LPP, K::EXACT, MEASURE>(x[k], nvalid, p);
+        bad |= !(conf[k] == conf[k]);
+      }
+      if constexpr (MEASURE == kEntropy) {
+        if (__any_sync(0xffffffffu, bad)) {  // rare: some pixel of this warp has a -inf / NaN logit
+#pragma unroll
+          for (int k = 0; k < PPT; ++k) conf[k] = conf_single<CL, LPP, K::EXACT, MEASURE, true>(x[k], nvalid, p);
+        }
+      }
+      if (plain) {
+        if (sub == 0) {
+#pragma unroll
+          for (int k = 0; k < PPT; ++k) acc.add(conf[k], p.fx_scale);
+        }
+      } else {
+#pragma unroll
+        for (int k = 0; k < PPT; ++k) {
+          const int l = k * G + pl;
+          int lbl = 0;
+          if (p.label) lbl = group_argmax<CL, LPP>(x[k], nvalid, class0);
+          if (sub == 0 && l < npix) emit_pixel(p, acc, conf[k], lbl, tile_pix0, off, l, in_img);
+        }
       }
     } else {
       float mu[PPT][CL];
@@ -581,7 +612,11 @@ __global__ void __launch_bounds__(kBlockThreads, Cfg<E, C, (MEASURE == kMulti)>:
       for (int k = 0; k < PPT; ++k) {
         const int l = k * G + pl;
         const float conf = conf_multi<CL, LPP, K::EXACT>(mu[k], m2s[k], nvalid, p);
-        if (sub == 0 && l < npix) emit_pixel(p, acc, conf, lbl[k], tile_pix0, off, l, in_img);
+        if (plain) {
+          if (sub == 0) acc.add(conf, p.fx_scale);
+        } else if (sub == 0 && l < npix) {
+          emit_pixel(p, acc, conf, lbl[k], tile_pix0, off, l, in_img);
+        }
       }
     }
   }
@@ -819,6 +854,7 @@ LaunchPlan plan_score(int dtype, int C, int measure, int T, long long total_pixe
 
 cudaError_t launch_score(const LaunchPlan& plan, int dtype, ScoreParams p, cudaStream_t stream) {
   if (p.total_pixels <= 0) return cudaSuccess;
+  p.any_out = (p.conf_map || p.label || p.mask) ? 1 : 0;
   cudaError_t err;
   if (plan.tiled) {
     p.stages = plan.stages;

@@ -17,6 +17,7 @@ struct ScoreParams {
   int C;
   int measure;
   int stages;
+  int any_out;  // conf_map || label || mask (set by launch_score)
   float inv_log2_c;  // 1 / log2(C): entropy in bits -> H / log(float32(C))   (active_learning.py:248-249)
   float threshold;  // alparams["threshold"]      (active_learning.py:265)
   float inv_T;
