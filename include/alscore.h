@@ -123,6 +123,39 @@ ALS_API int als_score_host(als_ctx* ctx, const void* logits, int dtype,
  */
 ALS_API int als_score_dlpack(als_ctx* ctx, void* managed, int measure, double* scores);
 
+/* ---- fused classifier head (replaces Final.call + active_learning.py:234-269) --------- */
+
+/*
+ * The logits scored above are produced by ENet's `Final` layer, a 3x3 stride-2 transposed
+ * convolution 16 -> C without bias (models/enet/enet_modules.py:1294-1381, called from
+ * models/enet/enet.py:367).  These entries take its INPUT feature map and its kernel instead of
+ * the logits: the contraction runs on the tensor cores (tcgen05, split-TF32 = fp32-level accuracy)
+ * inside the scoring kernel, so the [N,2h,2w,C] logits tensor is never written to or read from HBM.
+ *
+ * als_head_prepare: upload the layer's kernel.  `kernel` is HOST float32 [3][3][C][16]
+ * (tf.nn.conv2d_transpose filter layout [kh, kw, out_channels, in_channels], enet_modules.py:1341).
+ * ALS_ERR_UNSUPPORTED if no fused kernel is built for this class count (see als_head_supported).
+ */
+ALS_API int als_head_prepare(als_ctx* ctx, const float* kernel, int64_t C);
+
+/* 1 if a fused-head kernel exists for (C, measure), else 0. */
+ALS_API int als_head_supported(int64_t C, int measure);
+
+/*
+ * Score N images from their `Final`-layer input.
+ *   features   device f32 [N,h,w,16], dense NHWC, 16-byte aligned
+ *   scores     device f64[N]; conf_map / label / mask: optional device [N,2h,2w] as in als_score
+ * Same results as als_score on conv2d_transpose(features, kernel) (to fp32 rounding).
+ * Asynchronous on `stream`.
+ */
+ALS_API int als_score_features(als_ctx* ctx, const void* features, int64_t N, int64_t h, int64_t w, int measure,
+                       double* scores, float* conf_map, uint8_t* label, uint8_t* mask, float threshold,
+                       void* stream);
+
+/* :697-700 with the fused head: like als_pool_score_batch, from the `Final`-layer input (device or host). */
+ALS_API int als_pool_score_features_batch(als_ctx* ctx, const void* features, int features_on_host, int64_t B,
+                                  int64_t h, int64_t w, int measure, const int64_t* example_index);
+
 /* ---- loop-level boundary (replaces rank_confidence, active_learning.py:682-715) ---- */
 
 /* :684-685  confidence = np.zeros(num_examples, float32)  (device-resident). */

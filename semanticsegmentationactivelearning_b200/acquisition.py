@@ -190,6 +190,79 @@ class Scorer:
         return {"pseudo_confidence": conf, "pseudo_mean_confidence": scores, "pseudo_label": label,
                 "pseudo_mask": mask}
 
+    # -- fused classifier head (models/enet/enet_modules.py:1294-1381 + active_learning.py:234-269) ------
+    @staticmethod
+    def head_supported(num_classes: int, measure: str = "entropy") -> bool:
+        """True if a fused `Final`-head kernel is built for this class count."""
+        return bool(_lib.load().als_head_supported(int(num_classes), measure_id(measure)))
+
+    def prepare_head(self, kernel) -> None:
+        """Upload the `Final` layer's transposed-convolution kernel, float32 [3,3,C,16] (TF filter layout
+        [kh, kw, out_channels, in_channels], enet_modules.py:1341).  Needed once per weight update."""
+        k = np.ascontiguousarray(np.asarray(kernel, dtype=np.float32))
+        if k.ndim != 4 or k.shape[0] != 3 or k.shape[1] != 3 or k.shape[3] != 16:
+            raise ValueError("Final kernel must be [3,3,C,16], got %s" % (k.shape,))
+        self._check(self._lib.als_head_prepare(self._ctx, k.ctypes.data, int(k.shape[2])))
+        self._head_classes = int(k.shape[2])
+
+    def _features(self, features):
+        torch = _torch()
+        if torch is None or not isinstance(features, torch.Tensor) or not features.is_cuda:
+            raise TypeError("features must be a CUDA torch.Tensor [N,h,w,16] (host batches go through pool_score_features_batch)")
+        if features.dtype != torch.float32 or features.dim() != 4 or features.shape[-1] != 16 or not features.is_contiguous():
+            raise ValueError("features must be a dense float32 [N,h,w,16] tensor, got %s %s" % (features.dtype, tuple(features.shape)))
+        return torch, tuple(int(v) for v in features.shape[:3])
+
+    def score_features(self, features, measure: str = "entropy", *, out=None):
+        """pseudo_mean_confidence of the logits `Final` would produce from `features` [N,h,w,16] -- without
+        materialising them.  Returns a torch.float64 CUDA tensor [N] (asynchronous)."""
+        m = measure_id(measure)
+        torch, (n, h, w) = self._features(features)
+        if out is None:
+            out = torch.empty(n, dtype=torch.float64, device=features.device)
+        stream = torch.cuda.current_stream(features.device).cuda_stream
+        self._check(self._lib.als_score_features(self._ctx, features.data_ptr(), n, h, w, m, out.data_ptr(), None, None, None,
+                                                 0.0, C.c_void_p(stream)))
+        return out
+
+    def pseudo_annotation_features(self, features, measure: str = "entropy", threshold: float = 0.9):
+        """The PseudoAnnotation scope from the `Final`-layer input: dict like pseudo_annotation(), maps are [N,2h,2w]."""
+        m = measure_id(measure)
+        torch, (n, h, w) = self._features(features)
+        dev = features.device
+        shp = (n, 2 * h, 2 * w)
+        conf = torch.empty(shp, dtype=torch.float32, device=dev)
+        label = torch.empty(shp, dtype=torch.uint8, device=dev)
+        mask = torch.empty(shp, dtype=torch.uint8, device=dev)
+        scores = torch.empty(n, dtype=torch.float64, device=dev)
+        stream = torch.cuda.current_stream(dev).cuda_stream
+        self._check(self._lib.als_score_features(self._ctx, features.data_ptr(), n, h, w, m, scores.data_ptr(), conf.data_ptr(),
+                                                 label.data_ptr(), mask.data_ptr(), float(threshold), C.c_void_p(stream)))
+        return {"pseudo_confidence": conf, "pseudo_mean_confidence": scores, "pseudo_label": label, "pseudo_mask": mask}
+
+    def pool_score_features_batch(self, features, batch_indices, measure: str = "entropy") -> None:
+        """pool_score_batch from the `Final`-layer input [B,h,w,16] (CUDA tensor, or host tensor / array: staged)."""
+        m = measure_id(measure)
+        torch = _torch()
+        if torch is not None and isinstance(features, torch.Tensor):
+            if features.dtype != torch.float32 or not features.is_contiguous():
+                raise ValueError("features must be dense float32")
+            ptr, on_host, shape = features.data_ptr(), not features.is_cuda, tuple(features.shape)
+        elif isinstance(features, np.ndarray):
+            if features.dtype != np.float32 or not features.flags["C_CONTIGUOUS"]:
+                raise ValueError("features must be dense float32")
+            ptr, on_host, shape = features.ctypes.data, True, features.shape
+        else:
+            raise TypeError("features must be a torch.Tensor or numpy.ndarray")
+        if len(shape) != 4 or shape[-1] != 16:
+            raise ValueError("features must be [B,h,w,16], got %s" % (tuple(shape),))
+        idx = np.ascontiguousarray(np.asarray(batch_indices, dtype=np.int64))
+        if idx.shape != (shape[0],):
+            raise ValueError("batch_indices must have one entry per image (%d), got shape %s" % (shape[0], idx.shape))
+        self._keep = features
+        self._check(self._lib.als_pool_score_features_batch(self._ctx, ptr, 1 if on_host else 0, int(shape[0]), int(shape[1]),
+                                                            int(shape[2]), m, idx.ctypes.data))
+
     def score_dlpack(self, producer, measure: str = "entropy") -> np.ndarray:
         """Score any ``__dlpack__`` producer (TF >= 2.2, CuPy, JAX, NumPy, torch): device tensors
         zero-copy, host tensors staged.  Returns NumPy f64[N]."""
@@ -316,8 +389,11 @@ def _slice_images(logits, sl: slice):
 
 def rank_confidence(logits, unlabelled, selection_size: int, measure: str = "entropy", *,
                     batch_size: Optional[int] = None, example_index=None, num_examples: Optional[int] = None,
-                    dtype: Optional[str] = None, scorer: Optional[Scorer] = None):
+                    dtype: Optional[str] = None, scorer: Optional[Scorer] = None, head_kernel=None):
     """Drop-in for the ``rank_confidence()`` closure (active_learning.py:682-715).
+
+    With ``head_kernel`` (the `Final` layer's [3,3,C,16] kernel) the first argument is the layer's INPUT
+    feature map [N,h,w,16] (or batches of it) and the classifier head runs fused inside the scoring kernel.
 
     logits            the pool's logits [N,H,W,C] / [T,N,H,W,C] (device or host), or an iterable of
                       ``(batch_logits, batch_indices)`` pairs as ``sess.run`` would hand them out (:697-698)
@@ -348,7 +424,12 @@ def rank_confidence(logits, unlabelled, selection_size: int, measure: str = "ent
         batches = logits
         if num_examples is None:
             raise ValueError("num_examples is required when logits is an iterable of batches")
+    if head_kernel is not None:
+        sc.prepare_head(head_kernel)
     sc.pool_begin(int(num_examples))
     for batch_logits, batch_indices in batches:
-        sc.pool_score_batch(batch_logits, batch_indices, measure, dtype=dtype)
+        if head_kernel is not None:
+            sc.pool_score_features_batch(batch_logits, batch_indices, measure)
+        else:
+            sc.pool_score_batch(batch_logits, batch_indices, measure, dtype=dtype)
     return sc.pool_select(unlabelled, selection_size)

@@ -10,8 +10,8 @@ import sys
 PKG = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(PKG, "csrc")
 LIB = os.path.join(PKG, "libalscore.so")
-SOURCES = ["score.cu", "select.cu", "synth.cu", "capi.cu"]
-HEADERS = ["common.cuh", "score.cuh", "select.cuh", "synth.cuh", os.path.join("..", "..", "include", "alscore.h")]
+SOURCES = ["score.cu", "head.cu", "select.cu", "synth.cu", "capi.cu"]
+HEADERS = ["common.cuh", "pixel_math.cuh", "tc05.cuh", "head.cuh", "score.cuh", "select.cuh", "synth.cuh", os.path.join("..", "..", "include", "alscore.h")]
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
     "-Xcompiler", "-fPIC", "-Xcompiler", "-fvisibility=hidden",

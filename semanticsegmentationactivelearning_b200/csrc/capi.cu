@@ -10,6 +10,7 @@
 #include <vector>
 
 #include "../../include/alscore.h"
+#include "head.cuh"
 #include "score.cuh"
 #include "select.cuh"
 #include "synth.cuh"
@@ -72,6 +73,9 @@ struct als_ctx {
   // per-pixel output staging for the host path
   void* maps_dev = nullptr;
   size_t maps_cap = 0;
+  // fused classifier head: packed split-TF32 weights of `Final` (als_head_prepare)
+  float* head_weights = nullptr;
+  int64_t head_C = 0;
   // L2 flush scratch
   void* flush_buf = nullptr;
   size_t flush_bytes = 0;
@@ -363,7 +367,7 @@ int als_ctx_destroy(als_ctx* ctx) {
   if (ctx->copy_stream) cudaStreamSynchronize(ctx->copy_stream);
   void* ptrs[] = {ctx->acc, ctx->flags, ctx->tile_counter, ctx->scores_dev, ctx->index_dev, ctx->pool32, ctx->sel_ids, ctx->sel_keys,
                   ctx->sel_tmp_keys, ctx->sel_tmp_ids, ctx->sel_out_keys, ctx->sel_out_ids, ctx->stage[0], ctx->stage[1],
-                  ctx->maps_dev, ctx->flush_buf};
+                  ctx->maps_dev, ctx->flush_buf, ctx->head_weights};
   for (void* p : ptrs)
     if (p) cudaFree(p);
   for (int b = 0; b < 2; ++b) {
@@ -508,6 +512,166 @@ int als_score_dlpack(als_ctx* ctx, void* managed, int measure, double* scores) {
       return fail(ctx, ALS_ERR_INVALID, "unsupported DLPack device type %d", t.device.device_type);
   }
 }
+
+}  // extern "C"
+
+// ---- fused classifier head -----------------------------------------------------------------------
+
+namespace {
+
+int check_features(als_ctx* ctx, const void* features, int64_t N, int64_t h, int64_t w, int measure, bool want_label) {
+  if (!ctx) return fail(nullptr, ALS_ERR_INVALID, "context is NULL");
+  if (measure < ALS_ENTROPY || measure > ALS_VARIANCE)
+    return fail(ctx, ALS_ERR_UNSUPPORTED, "Uncertainty function not implemented.");
+  if (ctx->head_C <= 0) return fail(ctx, ALS_ERR_STATE, "als_head_prepare has not been called");
+  if (measure == ALS_VARIANCE) return fail(ctx, ALS_ERR_INVALID, "measure 'variance' needs T >= 2 Monte-Carlo samples");
+  if (!als_head_supported(ctx->head_C, measure))
+    return fail(ctx, ALS_ERR_UNSUPPORTED, "no fused-head kernel for C=%lld", (long long)ctx->head_C);
+  if (N < 0 || h < 1 || w < 1) return fail(ctx, ALS_ERR_INVALID, "bad feature shape [N=%lld,h=%lld,w=%lld,16]", (long long)N, (long long)h, (long long)w);
+  if (h > (1 << 20) || w > (1 << 20) || N > 0x7fffffff) return fail(ctx, ALS_ERR_INVALID, "feature map too large");
+  if (want_label && ctx->head_C > 256) return fail(ctx, ALS_ERR_INVALID, "uint8 pseudo_label needs C <= 256");
+  if (N > 0 && !features) return fail(ctx, ALS_ERR_INVALID, "features pointer is NULL");
+  if (reinterpret_cast<uintptr_t>(features) % 16 != 0) return fail(ctx, ALS_ERR_INVALID, "features must be 16-byte aligned");
+  return ALS_OK;
+}
+
+// device features [N,h,w,16] -> fixed-point sums -> finalize (scores64 and/or pool scatter)
+int score_features_device(als_ctx* ctx, const void* features, int64_t N, int64_t h, int64_t w, int measure, double* scores64,
+                          float* pool32, const long long* example_index_dev, int64_t num_examples, float* conf_map,
+                          uint8_t* label, uint8_t* mask, float threshold, cudaStream_t stream) {
+  if (N == 0) return ALS_OK;
+  const int C = static_cast<int>(ctx->head_C);
+  als::HeadPlan plan = als::plan_head(C, measure, ctx->num_sms);
+  if (!plan.func) return fail(ctx, ALS_ERR_UNSUPPORTED, "no fused-head kernel for C=%d", C);
+  if (plan.smem_bytes > ctx->max_smem) return fail(ctx, ALS_ERR_CUDA, "fused head needs %d bytes of shared memory", plan.smem_bytes);
+  const long long P = 4ll * h * w;  // output pixels per image (2h x 2w)
+  int shift = 62 - ceil_log2_ll(P);
+  if (shift > 44) shift = 44;
+  als::HeadParams p{};
+  p.sp.P = P;
+  p.sp.total_pixels = N * P;
+  p.sp.T = 1;
+  p.sp.C = C;
+  p.sp.measure = measure;
+  p.sp.inv_log2_c = static_cast<float>(1.0 / log2(static_cast<double>(C)));
+  p.sp.threshold = threshold;
+  p.sp.inv_T = 1.0f;
+  p.sp.fx_scale = ldexpf(1.0f, shift);
+  p.sp.acc = ctx->acc;
+  p.sp.acc_stride = ctx->acc_cap;
+  p.sp.flags = ctx->flags;
+  p.sp.tile_counter = ctx->tile_counter;
+  p.sp.conf_map = conf_map;
+  p.sp.label = label;
+  p.sp.mask = mask;
+  p.features = static_cast<const float*>(features);
+  p.weights = ctx->head_weights;
+  p.h = static_cast<int>(h);
+  p.w = static_cast<int>(w);
+  p.n_images = static_cast<int>(N);
+  p.n_strips = static_cast<int>((w + als::kHeadTileQuads - 1) / als::kHeadTileQuads);
+  // rows per unit: about 12 units per SM, 8..64 rows (one halo row is re-read per unit), evenly split
+  long long r = (N * h * p.n_strips) / (12ll * ctx->num_sms);
+  if (r < 8) r = 8;
+  if (r > 64) r = 64;
+  if (r > h) r = h;
+  const long long nrb = (h + r - 1) / r;
+  p.rows_per_unit = static_cast<int>((h + nrb - 1) / nrb);
+  p.n_rowblocks = static_cast<int>((h + p.rows_per_unit - 1) / p.rows_per_unit);
+  p.n_units = N * p.n_rowblocks * p.n_strips;
+  p.g = als::head_geometry(C);
+  ALS_CUDA(ctx, als::launch_head(plan, p, stream));
+  ALS_CUDA(ctx, als::launch_finalize(ctx->acc, ctx->acc_cap, ctx->flags, ctx->tile_counter, static_cast<int>(N),
+                                     ldexp(1.0, -shift) / static_cast<double>(P), scores64, pool32, example_index_dev,
+                                     num_examples, stream));
+  ctx->launches += 2;
+  return ALS_OK;
+}
+
+}  // namespace
+
+extern "C" {
+
+int als_head_supported(int64_t C, int measure) {
+  if (C < 2 || C > 32) return 0;
+  return als::plan_head(static_cast<int>(C), measure, 1).func != nullptr ? 1 : 0;
+}
+
+int als_head_prepare(als_ctx* ctx, const float* kernel, int64_t C) {
+  if (!ctx) return fail(nullptr, ALS_ERR_INVALID, "context is NULL");
+  if (!kernel) return fail(ctx, ALS_ERR_INVALID, "kernel pointer is NULL");
+  if (C < 2) return fail(ctx, ALS_ERR_INVALID, "need at least 2 classes, got C=%lld", (long long)C);
+  if (!als_head_supported(C, ALS_ENTROPY))
+    return fail(ctx, ALS_ERR_UNSUPPORTED, "no fused-head kernel is built for C=%lld (use als_score on the logits)", (long long)C);
+  DeviceGuard g(ctx->device);
+  const als::HeadGeom geom = als::head_geometry(static_cast<int>(C));
+  const size_t n = static_cast<size_t>(2) * 4 * geom.rows * 4;
+  std::vector<float> packed(n);
+  als::pack_head_weights(kernel, static_cast<int>(C), packed.data());
+  ALS_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+  if (ctx->head_weights) ALS_CUDA(ctx, cudaFree(ctx->head_weights));
+  ctx->head_weights = nullptr;
+  ctx->head_C = 0;
+  ALS_CUDA(ctx, cudaMalloc(reinterpret_cast<void**>(&ctx->head_weights), n * sizeof(float)));
+  ALS_CUDA(ctx, cudaMemcpy(ctx->head_weights, packed.data(), n * sizeof(float), cudaMemcpyHostToDevice));
+  ctx->head_C = C;
+  return ALS_OK;
+}
+
+int als_score_features(als_ctx* ctx, const void* features, int64_t N, int64_t h, int64_t w, int measure, double* scores,
+                       float* conf_map, uint8_t* label, uint8_t* mask, float threshold, void* stream) {
+  ALS_TRY(check_features(ctx, features, N, h, w, measure, label != nullptr));
+  if (N == 0) return ALS_OK;
+  if (!scores) return fail(ctx, ALS_ERR_INVALID, "scores pointer is NULL");
+  DeviceGuard g(ctx->device);
+  ALS_TRY(check_device_ptr(ctx, features, "features"));
+  ALS_TRY(check_device_ptr(ctx, scores, "scores"));
+  ALS_TRY(check_device_ptr(ctx, conf_map, "conf_map"));
+  ALS_TRY(check_device_ptr(ctx, label, "label"));
+  ALS_TRY(check_device_ptr(ctx, mask, "mask"));
+  ALS_TRY(ensure_acc(ctx, N));
+  cudaStream_t st = stream ? static_cast<cudaStream_t>(stream) : ctx->stream;
+  return score_features_device(ctx, features, N, h, w, measure, scores, nullptr, nullptr, 0, conf_map, label, mask, threshold, st);
+}
+
+int als_pool_score_features_batch(als_ctx* ctx, const void* features, int features_on_host, int64_t B, int64_t h, int64_t w,
+                                  int measure, const int64_t* example_index) {
+  ALS_TRY(check_features(ctx, features, B, h, w, measure, false));
+  if (ctx->pool_n < 0) return fail(ctx, ALS_ERR_STATE, "als_pool_begin has not been called");
+  if (B == 0) return ALS_OK;
+  if (!example_index) return fail(ctx, ALS_ERR_INVALID, "example_index is NULL");
+  for (int64_t i = 0; i < B; ++i)
+    if (example_index[i] < 0 || example_index[i] >= ctx->pool_n)
+      return fail(ctx, ALS_ERR_INVALID, "example_index[%lld]=%lld out of range [0, %lld)", (long long)i,
+                  (long long)example_index[i], (long long)ctx->pool_n);
+  DeviceGuard g(ctx->device);
+  ALS_TRY(ensure_acc(ctx, B));
+  ALS_TRY(grow(ctx, &ctx->index_dev, &ctx->index_cap, B, false));
+  const void* dev = features;
+  int b = -1;
+  if (features_on_host) {
+    const Shape s{1, B, h, w, als::kHeadChannels};
+    ALS_TRY(ensure_stage(ctx, static_cast<size_t>(s.elems()) * 4));
+    ALS_TRY(stage_chunk(ctx, static_cast<const unsigned char*>(features), s, 4, 0, B, &b));
+    ALS_CUDA(ctx, cudaStreamWaitEvent(ctx->stream, ctx->ev_copied[b], 0));
+    dev = ctx->stage[b];
+  } else {
+    ALS_TRY(check_device_ptr(ctx, features, "features"));
+  }
+  ALS_CUDA(ctx, cudaMemcpyAsync(ctx->index_dev, example_index, static_cast<size_t>(B) * sizeof(int64_t),
+                                cudaMemcpyHostToDevice, ctx->stream));
+  ALS_TRY(score_features_device(ctx, dev, B, h, w, measure, nullptr, ctx->pool32, ctx->index_dev, ctx->pool_n, nullptr, nullptr,
+                                nullptr, 0.f, ctx->stream));
+  if (b >= 0) {
+    ALS_CUDA(ctx, cudaEventRecord(ctx->ev_scored[b], ctx->stream));
+    ALS_CUDA(ctx, cudaEventSynchronize(ctx->ev_copied[b]));
+  }
+  return ALS_OK;
+}
+
+}  // extern "C"
+
+extern "C" {
 
 // ---- rank_confidence-shaped pool API -----------------------------------------------------------
 

@@ -1,0 +1,453 @@
+// Fused ENet classifier head + pool scoring for sm_100a: the logits never reach HBM.
+//
+// Reference: `Final.call` (/root/reference/models/enet/enet_modules.py:1359-1381) is a 3x3 stride-2
+// transposed convolution 16 -> C without bias that turns the last feature map [N,h,w,16] into the logits
+// [N,2h,2w,C] scored by active_learning.py:239-263.  Reading 16 B of features per OUTPUT pixel instead of
+// 4*C B of logits removes the HBM bound of score.cu; the contraction (2.25*16*C MAC per output pixel) runs
+// on the 5th-generation tensor cores, the softmax / confidence math on the CUDA cores straight out of
+// tensor memory.
+//
+// GEMM view.  Input pixel (i,j) owns the output quad (2i+dy, 2j+dx).  With SAME padding (extra row /
+// column at the bottom / right) the quad depends on the four input pixels (i-oy, j-ox), oy,ox in {0,1}:
+//   out(0,0) = Y[i,j]K00 + Y[i-1,j]K20 + Y[i,j-1]K02 + Y[i-1,j-1]K22      out(0,1) = Y[i,j]K01 + Y[i-1,j]K21
+//   out(1,0) = Y[i,j]K10 + Y[i,j-1]K12                                     out(1,1) = Y[i,j]K11
+// A tile is 128 consecutive input pixels of one row (UMMA M = 128); its accumulator has one block of
+// CB = round_up(C,4) columns per quad pixel, in the order (0,1) (0,0) (1,0) (1,1) so that every source
+// pixel contributes to ONE contiguous column range: four narrow MMAs (N = 4CB, 2CB, 2CB, CB rounded up to
+// 16) instead of one 64 x 4C GEMM that is 44 % zeros.
+//
+// Precision.  kind::tf32 keeps 11 significand bits, the parity bar is 1e-5 on confidences, so both
+// operands are split x = hi + lo (hi = tf32(x), lo = tf32(x - hi)) and three products are accumulated in
+// fp32: hi*lo + lo*hi + hi*hi (the dropped lo*lo term and the tf32 rounding of the lo parts are ~2^-24 relative each).
+//
+// Data movement.  One 1-D bulk copy (TMA engine, UBLKCP) per feature row segment of 129 pixels (one halo
+// pixel on the left) into a raw ring; two "splitter" warps rewrite it as the canonical K-major no-swizzle
+// UMMA operand (16-byte chunk planes, see tc05.cuh), hi and lo, where a matrix shifted by one pixel is the
+// same buffer + 16 bytes -- so the (j-1) operands need no second copy.  A CTA walks down a strip of 128
+// columns: each feature row is loaded once and used by two consecutive tiles (as row i, then as row i-1).
+//
+// Roles (640 threads, 1 CTA / SM, persistent, static round-robin over units of R rows x 128 columns):
+//   warp 0      producer: bulk copies                  warp 1      MMA issuer (one lane), TMEM owner
+//   warps 2-3   splitters: raw -> hi/lo operands       warps 4-19  epilogue: 4 accumulator stages x 4 lane quarters
+#include "head.cuh"
+
+#include <math.h>
+#include <string.h>
+
+#include "common.cuh"
+#include "pixel_math.cuh"
+#include "tc05.cuh"
+
+namespace als {
+
+namespace {
+
+constexpr int kRawStages = 4;
+constexpr int kCanStages = 4;
+constexpr int kAccStages = 4;
+constexpr int kAccCols = 128;                         // TMEM columns per accumulator stage
+constexpr int kSlotPx = kHeadTileQuads + 1;           // 129 pixels: one halo pixel on the left
+constexpr int kRawSlotBytes = 8320;                   // 129 * 64 rounded up to 128
+constexpr int kPlaneBytes = (kSlotPx + 1) * 16;       // 2080: stride between 16-byte chunk planes (LBO of A)
+constexpr int kPartBytes = 4 * kPlaneBytes;           // 8320: one precision part (hi or lo) of a row
+constexpr int kCanSlotBytes = 2 * kPartBytes;         // 16640
+constexpr int kHeadThreads = 640;
+constexpr int kHeaderBytes = 512;
+constexpr int kFirstEpilogueWarp = 4;
+
+struct RawMeta {
+  int valid;  // quad columns of this strip that exist (<= 128)
+  int first;  // strip starts at image column 0: the halo pixel is padding
+  int zero;   // whole row is padding (row -1 of the image)
+  int pad_;
+};
+
+struct Unit {
+  int n, i0, rows, j0, valid;
+};
+
+__device__ __forceinline__ Unit decode_unit(const HeadParams& p, long long u) {
+  Unit un;
+  const int strip = static_cast<int>(u % p.n_strips);
+  const long long v = u / p.n_strips;
+  const int rb = static_cast<int>(v % p.n_rowblocks);
+  un.n = static_cast<int>(v / p.n_rowblocks);
+  un.i0 = rb * p.rows_per_unit;
+  un.rows = min(p.rows_per_unit, p.h - un.i0);
+  un.j0 = strip * kHeadTileQuads;
+  un.valid = min(kHeadTileQuads, p.w - un.j0);
+  return un;
+}
+
+// TMEM -> registers, CNT consecutive columns (CNT multiple of 4, <= 32)
+template <int CNT>
+__device__ __forceinline__ void ld_cols(uint32_t taddr, float (&v)[CNT]) {
+  static_assert(CNT % 4 == 0 && CNT >= 4 && CNT <= 32, "column count");
+  uint32_t r[CNT];
+  int done = 0;
+  if constexpr (CNT == 32) {
+    float t[32];
+    tc05::ld32(taddr, t);
+#pragma unroll
+    for (int i = 0; i < 32; ++i) v[i] = t[i];
+    return;
+  }
+  if constexpr (CNT & 16) {
+    float t[16];
+    tc05::ld16(taddr + done, t);
+#pragma unroll
+    for (int i = 0; i < 16; ++i) v[done + i] = t[i];
+    done += 16;
+  }
+  if constexpr (CNT & 8) {
+    float t[8];
+    tc05::ld8(taddr + done, t);
+#pragma unroll
+    for (int i = 0; i < 8; ++i) v[done + i] = t[i];
+    done += 8;
+  }
+  if constexpr (CNT & 4) {
+    asm volatile("tcgen05.ld.sync.aligned.32x32b.x4.b32 {%0,%1,%2,%3}, [%4];"
+                 : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3])
+                 : "r"(taddr + done)
+                 : "memory");
+#pragma unroll
+    for (int i = 0; i < 4; ++i) v[done + i] = __uint_as_float(r[i]);
+  }
+}
+
+}  // namespace
+
+template <int C, int MEASURE>
+__global__ void __launch_bounds__(kHeadThreads, 1) score_head_kernel(const HeadParams p) {
+  constexpr int CB = (C + 3) & ~3;
+  extern __shared__ __align__(128) unsigned char smem[];
+  uint64_t* full_raw = reinterpret_cast<uint64_t*>(smem);
+  uint64_t* empty_raw = full_raw + kRawStages;
+  uint64_t* full_can = empty_raw + kRawStages;
+  uint64_t* empty_can = full_can + kCanStages;
+  uint64_t* full_acc = empty_can + kCanStages;
+  uint64_t* empty_acc = full_acc + kAccStages;
+  uint64_t* wbar = empty_acc + kAccStages;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + 256);
+  RawMeta* meta = reinterpret_cast<RawMeta*>(smem + 320);
+  unsigned char* raw_base = smem + kHeaderBytes;
+  unsigned char* can_base = raw_base + kRawStages * kRawSlotBytes;
+  unsigned char* w_base = can_base + kCanStages * kCanSlotBytes;
+  const int lbo_b = p.g.rows * 16;      // bytes between chunk planes of the packed weights
+  const int wpart_bytes = 4 * lbo_b;    // one precision part of the weights
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < kRawStages; ++s) {
+      mbar_init(&full_raw[s], 1);
+      mbar_init(&empty_raw[s], 2);
+    }
+    for (int s = 0; s < kCanStages; ++s) {
+      mbar_init(&full_can[s], 2);
+      mbar_init(&empty_can[s], 1);
+    }
+    for (int s = 0; s < kAccStages; ++s) {
+      mbar_init(&full_acc[s], 1);
+      mbar_init(&empty_acc[s], 4);
+    }
+    mbar_init(wbar, 1);
+    fence_mbar_init();
+  }
+  if (warp == 1) tc05::tmem_alloc<kAccStages * kAccCols>(tmem_slot);
+  tc05::fence_before_sync();
+  __syncthreads();
+  tc05::fence_after_sync();
+  const uint32_t tmem = *tmem_slot;
+
+  if (warp == 0) {
+    // ===== producer =====
+    if (lane == 0) {
+      const uint64_t policy = l2_policy_evict_first();
+      mbar_arrive_expect_tx(wbar, 2u * wpart_bytes);
+      bulk_g2s(w_base, p.weights, 2u * wpart_bytes, wbar, policy);
+      int s = 0;
+      uint32_t ph = 0;
+      for (long long u = blockIdx.x; u < p.n_units; u += gridDim.x) {
+        const Unit un = decode_unit(p, u);
+        const int first = un.j0 == 0 ? 1 : 0;
+        for (int r = -1; r < un.rows; ++r) {
+          const int row = un.i0 + r;
+          mbar_wait(&empty_raw[s], ph ^ 1u);
+          meta[s].valid = un.valid;
+          meta[s].first = first;
+          meta[s].zero = row < 0 ? 1 : 0;
+          if (row < 0) {
+            mbar_arrive_expect_tx(&full_raw[s], 0);
+          } else {
+            const float* src = p.features +
+                               ((static_cast<long long>(un.n) * p.h + row) * p.w + (un.j0 - (first ? 0 : 1))) * kHeadChannels;
+            const uint32_t bytes = static_cast<uint32_t>(un.valid + (first ? 0 : 1)) * 64u;
+            unsigned char* dst = raw_base + s * kRawSlotBytes + (first ? 64 : 0);
+            mbar_arrive_expect_tx(&full_raw[s], bytes);
+            bulk_g2s(dst, src, bytes, &full_raw[s], policy);
+          }
+          if (++s == kRawStages) { s = 0; ph ^= 1u; }
+        }
+      }
+    }
+    __syncwarp();
+  } else if (warp == 1) {
+    // ===== MMA issuer =====
+    if (lane == 0) {
+      uint32_t idesc[4];
+#pragma unroll
+      for (int o = 0; o < 4; ++o) idesc[o] = tc05::idesc_tf32(kHeadTileQuads, p.g.n[o]);
+      const uint32_t can_addr = smem_u32(can_base);
+      const uint32_t w_addr = smem_u32(w_base);
+      mbar_wait(wbar, 0);
+      long long seq = 0;  // canonical rows consumed so far (ring position)
+      long long tile = 0;
+      for (long long u = blockIdx.x; u < p.n_units; u += gridDim.x) {
+        const Unit un = decode_unit(p, u);
+        // halo row of the unit
+        mbar_wait(&full_can[seq % kCanStages], static_cast<uint32_t>((seq / kCanStages) & 1));
+        for (int k = 0; k < un.rows; ++k) {
+          const long long sp = seq + k, sc = seq + k + 1;
+          const int slot_prev = static_cast<int>(sp % kCanStages), slot_cur = static_cast<int>(sc % kCanStages);
+          mbar_wait(&full_can[slot_cur], static_cast<uint32_t>((sc / kCanStages) & 1));
+          const int a = static_cast<int>(tile % kAccStages);
+          mbar_wait(&empty_acc[a], static_cast<uint32_t>(((tile / kAccStages) & 1) ^ 1));
+          tc05::fence_after_sync();
+          const uint32_t d = tmem + a * kAccCols;
+          bool acc = false;
+#pragma unroll
+          // The small cross terms go first and the hi*hi products last: the tensor core truncates when it adds
+          // into the accumulator, so every MMA issued after the accumulator has reached full scale costs
+          // ~2^-24 of it -- 8 such steps this way round instead of 24.
+          for (int pc = 0; pc < 3; ++pc) {  // hi*lo, lo*hi, hi*hi
+            const uint32_t a_part = (pc == 1) ? kPartBytes : 0;
+            const uint32_t b_part = (pc == 0) ? wpart_bytes : 0;
+#pragma unroll
+            for (int o = 0; o < 4; ++o) {
+              const uint32_t a0 = can_addr + ((o & 1) ? slot_prev : slot_cur) * kCanSlotBytes + a_part + ((o < 2) ? 16u : 0u);
+              const uint32_t b0 = w_addr + b_part + p.g.row0[o] * 16;
+#pragma unroll
+              for (int ks = 0; ks < 2; ++ks) {
+                tc05::mma_tf32(d + p.g.col0[o], tc05::smem_desc(a0 + ks * 2 * kPlaneBytes, kPlaneBytes, 128),
+                               tc05::smem_desc(b0 + ks * 2 * lbo_b, lbo_b, 128), idesc[o], acc);
+                acc = true;
+              }
+            }
+          }
+          tc05::commit(&full_acc[a]);
+          tc05::commit(&empty_can[slot_prev]);
+          if (k == un.rows - 1) tc05::commit(&empty_can[slot_cur]);
+          ++tile;
+        }
+        seq += un.rows + 1;
+      }
+    }
+    __syncwarp();
+  } else if (warp < kFirstEpilogueWarp) {
+    // ===== splitters: raw NHWC row -> canonical hi / lo operand planes =====
+    const int st = threadIdx.x - 64;
+    int s = 0, c = 0;
+    uint32_t phs = 0, phc = 0;
+    for (long long u = blockIdx.x; u < p.n_units; u += gridDim.x) {
+      const Unit un = decode_unit(p, u);
+      for (int r = -1; r < un.rows; ++r) {
+        mbar_wait(&full_raw[s], phs);
+        const RawMeta m = meta[s];
+        mbar_wait(&empty_can[c], phc ^ 1u);
+        const unsigned char* raw = raw_base + s * kRawSlotBytes;
+        unsigned char* hi = can_base + c * kCanSlotBytes;
+        const int lo_px = m.first ? 1 : 0;
+#pragma unroll 3
+        for (int q = st; q < kSlotPx * 4; q += 64) {
+          const int px = q >> 2, ch = q & 3;
+          float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+          if (!m.zero && px >= lo_px && px <= m.valid) v = *reinterpret_cast<const float4*>(raw + q * 16);
+          float4 vh, vl;
+          vh.x = tc05::round_tf32(v.x); vh.y = tc05::round_tf32(v.y); vh.z = tc05::round_tf32(v.z); vh.w = tc05::round_tf32(v.w);
+          vl.x = tc05::round_tf32(v.x - vh.x); vl.y = tc05::round_tf32(v.y - vh.y);
+          vl.z = tc05::round_tf32(v.z - vh.z); vl.w = tc05::round_tf32(v.w - vh.w);
+          unsigned char* dst = hi + ch * kPlaneBytes + px * 16;
+          *reinterpret_cast<float4*>(dst) = vh;
+          *reinterpret_cast<float4*>(dst + kPartBytes) = vl;
+        }
+        tc05::fence_proxy_async();
+        __syncwarp();
+        if (lane == 0) {
+          mbar_arrive(&full_can[c]);
+          mbar_arrive(&empty_raw[s]);
+        }
+        if (++s == kRawStages) { s = 0; phs ^= 1u; }
+        if (++c == kCanStages) { c = 0; phc ^= 1u; }
+      }
+    }
+  } else {
+    // ===== epilogue: tensor memory -> confidences -> per-image sums =====
+    const int e = warp - kFirstEpilogueWarp;
+    const int a = e >> 2;        // accumulator stage this warp serves
+    const int quarter = warp & 3;  // TMEM lane quarter this warp may read
+    const int m = quarter * 32 + lane;
+    const uint32_t tbase = tmem + (static_cast<uint32_t>(quarter * 32) << 16) + a * kAccCols;
+    const ScoreParams& sp = p.sp;
+    const int W = 2 * p.w;
+    ImageAcc acc;
+    long long tile = 0;
+    for (long long u = blockIdx.x; u < p.n_units; u += gridDim.x) {
+      const Unit un = decode_unit(p, u);
+      if (un.n != acc.img) {
+        acc.flush(sp);
+        acc.img = un.n;
+      }
+      const bool valid = m < un.valid;
+      for (int k = 0; k < un.rows; ++k, ++tile) {
+        if ((tile % kAccStages) != a) continue;
+        mbar_wait(&full_acc[a], static_cast<uint32_t>((tile / kAccStages) & 1));
+        tc05::fence_after_sync();
+        float conf[4];
+        int lbl[4];
+#pragma unroll
+        for (int b = 0; b < 4; ++b) {
+          float v[CB];
+          ld_cols<CB>(tbase + b * CB, v);
+          tc05::ld_wait();
+          if (b == 3) {  // everything is in registers: hand the accumulator back to the MMA warp
+            tc05::fence_before_sync();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&empty_acc[a]);
+          }
+          float x[C];
+#pragma unroll
+          for (int j = 0; j < C; ++j) x[j] = v[j];
+          lbl[b] = sp.label ? group_argmax<C, 1>(x, C, 0) : 0;
+          conf[b] = conf_single<C, 1, true, MEASURE>(x, C, sp);
+          if constexpr (MEASURE == kEntropy) {
+            if (__any_sync(0xffffffffu, !(conf[b] == conf[b])))  // rare: -inf / NaN logits
+              conf[b] = conf_single<C, 1, true, MEASURE, true>(x, C, sp);
+          }
+        }
+        if (valid) {
+#pragma unroll
+          for (int b = 0; b < 4; ++b) acc.add(conf[b], sp.fx_scale);
+          if (sp.any_out) {
+            const int i = un.i0 + k;
+#pragma unroll
+            for (int b = 0; b < 4; ++b) {
+              const int dy = b >> 1, dx = (b == 0 || b == 3) ? 1 : 0;  // blocks: (0,1) (0,0) (1,0) (1,1)
+              const long long g = (static_cast<long long>(un.n) * (2 * p.h) + (2 * i + dy)) * W + 2 * (un.j0 + m) + dx;
+              if (sp.conf_map) sp.conf_map[g] = conf[b];
+              if (sp.mask) sp.mask[g] = (conf[b] < sp.threshold) ? 0 : 1;  // active_learning.py:265-269
+              if (sp.label) sp.label[g] = static_cast<uint8_t>(lbl[b]);
+            }
+          }
+        }
+      }
+    }
+    acc.flush(sp);
+  }
+
+  tc05::fence_before_sync();
+  __syncthreads();
+  if (warp == 1) tc05::tmem_dealloc<kAccStages * kAccCols>(tmem);
+}
+
+// ---- host side -------------------------------------------------------------------------------------
+static int round_up(int v, int m) { return (v + m - 1) / m * m; }
+
+HeadGeom head_geometry(int C) {
+  HeadGeom g{};
+  g.C = C;
+  g.CB = round_up(C, 4);
+  const int CB = g.CB;
+  g.n[1] = round_up(2 * CB, 16);  g.col0[1] = 0;    // source (i-1, j)   -> blocks 0,1
+  g.n[2] = round_up(2 * CB, 16);  g.col0[2] = CB;   // source (i, j-1)   -> blocks 1,2
+  g.n[3] = round_up(CB, 16);      g.col0[3] = CB;   // source (i-1, j-1) -> block 1
+  int n0 = round_up(4 * CB, 16);                    // source (i, j)     -> blocks 0..3; also initialises every column
+  for (int o = 1; o < 4; ++o)
+    if (g.col0[o] + g.n[o] > n0) n0 = round_up(g.col0[o] + g.n[o], 16);
+  g.n[0] = n0;
+  g.col0[0] = 0;
+  int r = 0;
+  for (int o = 0; o < 4; ++o) {
+    g.row0[o] = r;
+    r += g.n[o];
+  }
+  g.rows = r;
+  return g;
+}
+
+static float host_round_tf32(float x) {
+  uint32_t u;
+  memcpy(&u, &x, 4);
+  if ((u & 0x7f800000u) == 0x7f800000u) return x;  // inf / nan unchanged
+  u = (u + 0x1000u) & 0xffffe000u;                 // round to nearest, ties away (cvt.rna.tf32.f32)
+  memcpy(&x, &u, 4);
+  return x;
+}
+
+size_t pack_head_weights(const float* kernel, int C, float* out) {
+  const HeadGeom g = head_geometry(C);
+  // tap (ky,kx) of source o for block b, -1 = none.  Filter layout [ky][kx][c][ch]  (enet_modules.py:1341)
+  static const int tap[4][4][2] = {
+      {{0, 1}, {0, 0}, {1, 0}, {1, 1}},      // Y[i, j]
+      {{2, 1}, {2, 0}, {-1, -1}, {-1, -1}},  // Y[i-1, j]
+      {{-1, -1}, {0, 2}, {1, 2}, {-1, -1}},  // Y[i, j-1]
+      {{-1, -1}, {2, 2}, {-1, -1}, {-1, -1}},  // Y[i-1, j-1]
+  };
+  const size_t part = static_cast<size_t>(4) * g.rows * 4;  // floats per precision part
+  for (size_t i = 0; i < 2 * part; ++i) out[i] = 0.f;
+  for (int o = 0; o < 4; ++o)
+    for (int nn = 0; nn < g.n[o]; ++nn) {
+      const int col = g.col0[o] + nn;
+      const int b = col / g.CB, c = col % g.CB;
+      if (b >= 4 || c >= C || tap[o][b][0] < 0) continue;
+      const float* w = kernel + ((static_cast<size_t>(tap[o][b][0]) * 3 + tap[o][b][1]) * C + c) * kHeadChannels;
+      const int row = g.row0[o] + nn;
+      for (int k = 0; k < kHeadChannels; ++k) {
+        const float hi = host_round_tf32(w[k]);
+        const float lo = host_round_tf32(w[k] - hi);
+        const size_t at = (static_cast<size_t>(k / 4) * g.rows + row) * 4 + (k % 4);
+        out[at] = hi;
+        out[part + at] = lo;
+      }
+    }
+  return 2 * part;
+}
+
+template <int C>
+static const void* pick_head(int measure, const char** name) {
+  switch (measure) {
+    case kEntropy: *name = "score_head_kernel<entropy>"; return (const void*)score_head_kernel<C, kEntropy>;
+    case kMargin: *name = "score_head_kernel<margin>"; return (const void*)score_head_kernel<C, kMargin>;
+    case kConfidence: *name = "score_head_kernel<confidence>"; return (const void*)score_head_kernel<C, kConfidence>;
+    default: return nullptr;
+  }
+}
+
+HeadPlan plan_head(int C, int measure, int num_sms) {
+  HeadPlan plan{};
+  switch (C) {
+    case 6: plan.func = pick_head<6>(measure, &plan.name); break;
+    case 19: plan.func = pick_head<19>(measure, &plan.name); break;
+    default: plan.func = nullptr; break;
+  }
+  if (!plan.func) return plan;
+  const HeadGeom g = head_geometry(C);
+  plan.block = kHeadThreads;
+  plan.grid = num_sms;
+  plan.smem_bytes = kHeaderBytes + kRawStages * kRawSlotBytes + kCanStages * kCanSlotBytes + 2 * 4 * g.rows * 16;
+  return plan;
+}
+
+cudaError_t launch_head(const HeadPlan& plan, HeadParams p, cudaStream_t stream) {
+  if (p.n_units <= 0) return cudaSuccess;
+  p.sp.any_out = (p.sp.conf_map || p.sp.label || p.sp.mask) ? 1 : 0;
+  cudaError_t err = cudaFuncSetAttribute(plan.func, cudaFuncAttributeMaxDynamicSharedMemorySize, plan.smem_bytes);
+  if (err != cudaSuccess) return err;
+  const long long grid = p.n_units < plan.grid ? p.n_units : plan.grid;
+  void* args[] = {&p};
+  return cudaLaunchKernel(plan.func, dim3(static_cast<unsigned>(grid)), dim3(plan.block), args, plan.smem_bytes, stream);
+}
+
+}  // namespace als
