@@ -49,6 +49,14 @@ WORKLOADS = {
                    desc="PseudoAnnotation scope with per-pixel outputs (conf+label+mask), batches of 8 @512x1024, C=19"),
     "train64": dict(N=512, T=1, H=512, W=1024, C=19, measure="entropy", resident=512, chunk=64, maps=True,
                     desc="PseudoAnnotation scope with per-pixel outputs (conf+label+mask), batches of 64 @512x1024, C=19"),
+    # fused classifier head: the scorer is fed the `Final` layer's INPUT [N,h,w,16]
+    # (16 B per output pixel instead of 4*C) and runs the 16->C transposed convolution on the tensor cores itself
+    "cfg1h": dict(N=2975, T=1, H=512, W=1024, C=19, measure="entropy", resident=2975, chunk=425, head=True,
+                  desc="fused Final head + entropy, pool 2975 @512x1024 (features 256x512x16), C=19"),
+    "cfg3h": dict(N=372, T=1, H=1024, W=2048, C=19, measure="margin", resident=372, chunk=124, head=True,
+                  desc="fused Final head + margin @1024x2048 (features 512x1024x16), 372 images per GPU"),
+    "cfg4h": dict(N=4096, T=1, H=480, W=640, C=6, measure="entropy", resident=4096, chunk=512, head=True,
+                  desc="fused Final head + entropy @480x640 (features 240x320x16), C=6, pool 4096"),
 }
 K_SELECT = 50          # conf/enet_cityscapes_active_learning.json:59
 SEED = 20191013
@@ -240,10 +248,24 @@ def main():
     id0 = rank * N                                    # this rank's global example ids: [id0, id0 + N)
 
     sc = Scorer(local_rank)
-    # resident logits [T, resident, H, W, C]; chunks are dense [T, chunk, ...] tensors of their own
+    head = bool(w.get("head"))
     n_chunk_bufs = resident // chunk
-    bufs = [sc.synth_logits(T, id0 + i * chunk, chunk, H, W, C, dtype=dtype, seed=SEED, squeeze_t=False)
-            for i in range(n_chunk_bufs)]
+    if head:
+        # resident `Final`-layer inputs [chunk, H/2, W/2, 16] (random-init features and kernel, seeded)
+        if args.dtype != "f32" or T != 1:
+            raise SystemExit("the fused-head workloads are fp32, T=1")
+        gen = torch.Generator(device=dev); gen.manual_seed(SEED + rank)
+        head_kernel = (0.4 * np.random.default_rng(SEED).standard_normal((3, 3, C, 16))).astype(np.float32)
+        sc.prepare_head(head_kernel)
+        bufs = []
+        for i in range(n_chunk_bufs):
+            f = torch.randn((chunk, H // 2, W // 2, 16), generator=gen, device=dev, dtype=torch.float32)
+            f *= 0.3 + torch.rand((chunk, 1, 1, 1), generator=gen, device=dev)
+            bufs.append(f)
+    else:
+        # resident logits [T, resident, H, W, C]; chunks are dense [T, chunk, ...] tensors of their own
+        bufs = [sc.synth_logits(T, id0 + i * chunk, chunk, H, W, C, dtype=dtype, seed=SEED, squeeze_t=False)
+                for i in range(n_chunk_bufs)]
     torch.cuda.synchronize()
     # pool chunk list: (buffer, first local id, count)
     chunks = []
@@ -251,7 +273,9 @@ def main():
     while n0 < N:
         nb = min(chunk, N - n0)
         buf = bufs[(n0 // chunk) % n_chunk_bufs]
-        if nb < chunk:   # ragged tail: a dense [T, nb] tensor of its own
+        if nb < chunk and head:
+            buf = buf[:nb]
+        elif nb < chunk:   # ragged tail: a dense [T, nb] tensor of its own
             buf = sc.synth_logits(T, id0 + n0, nb, H, W, C, dtype=dtype, seed=SEED, squeeze_t=False)
         chunks.append((buf, n0, nb))
         n0 += nb
@@ -270,7 +294,9 @@ def main():
             if record:
                 e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
                 e0.record()
-            if maps:
+            if head:
+                sc.pool_score_features_batch(buf, idx, measure)
+            elif maps:
                 map_outs[nb] = sc.pseudo_annotation(buf if T > 1 else buf[0], measure, 0.9, out=map_outs.get(nb))
             else:
                 sc.pool_score_batch(buf, idx, measure)
@@ -317,26 +343,31 @@ def main():
     full = [(a.elapsed_time(b), nb) for a, b, nb in ev_pairs if nb == chunk] or [(a.elapsed_time(b), nb) for a, b, nb in ev_pairs]
     avg_ms = sum(m for m, _ in full) / len(full)
     bytes_launch = full[0][1] * P * (T * C * es + out_bytes_pix)
+    if head:
+        bytes_launch = full[0][1] * (P // 4) * 64          # 16 fp32 channels per INPUT pixel = 16 B per output pixel
     peak, peak_src = load_peaks()
     achieved = bytes_launch / (avg_ms * 1e-3) / 1e9
     kernel_share = sum(a.elapsed_time(b) for a, b, _ in ev_pairs) / ms_total
 
     # ---- diagnostic: the scoring kernel alone, launched back to back on one chunk (host latency hidden) ----
     burst_buf = chunks[0][0]
-    burst_in = burst_buf if T > 1 else burst_buf[0]
+    burst_in = burst_buf if (T > 1 or head) else burst_buf[0]
     burst_out = torch.empty(chunks[0][2], dtype=torch.float64, device=dev)
     n_burst = max(4, min(40, int(0.25 / max(avg_ms * 1e-3, 1e-5))))
+    burst_fn = (lambda: sc.score_features(burst_in, measure, out=burst_out)) if head else \
+               (lambda: sc.score(burst_in, measure, out=burst_out))
     for _ in range(3):
-        sc.score(burst_in, measure, out=burst_out)
+        burst_fn()
     torch.cuda.synchronize()
     b0, b1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     b0.record()
     for _ in range(n_burst):
-        sc.score(burst_in, measure, out=burst_out)
+        burst_fn()
     b1.record()
     torch.cuda.synchronize()
     burst_ms = b0.elapsed_time(b1) / n_burst
-    burst = {"launches": n_burst, "avg_ms": burst_ms, "GBps": chunks[0][2] * T * P * C * es / (burst_ms * 1e-3) / 1e9,
+    burst = {"launches": n_burst, "avg_ms": burst_ms, "GBps": bytes_launch / (burst_ms * 1e-3) / 1e9,
+             "Gpix_s": chunks[0][2] * P / (burst_ms * 1e-3) / 1e9,
              "outputs": "scores only",
              "note": "score+finalize launched back to back on one resident chunk, outside the timed region"}
 
@@ -344,19 +375,23 @@ def main():
     e2e = None
     if not args.no_e2e and not maps:
         from semanticsegmentationactivelearning_b200 import rank_confidence
-        per_img = T * P * C * es
+        per_img = (P // 4) * 64 if head else T * P * C * es
         bsz = max(1, min(8, int((2 << 30) // per_img)))              # images per sess.run-like batch (<= 8, :689)
         n_e2e = max(bsz, min(N, int((8 << 30) // per_img) // bsz * bsz))   # ~8 GB of logits per step
         tdt = torch.float32 if args.dtype == "f32" else torch.bfloat16
-        host = torch.empty((T, bsz, H, W, C), dtype=tdt).pin_memory()
-        host.copy_(bufs[0][:, :bsz])
+        if head:
+            host = torch.empty((bsz, H // 2, W // 2, 16), dtype=tdt).pin_memory()
+            host.copy_(bufs[0][:bsz])
+        else:
+            host = torch.empty((T, bsz, H, W, C), dtype=tdt).pin_memory()
+            host.copy_(bufs[0][:, :bsz])
         torch.cuda.synchronize()
-        host_np_batches = None
 
         def e2e_step():
-            batches = ((host if T > 1 else host[0], np.arange(i, i + bsz, dtype=np.int64)) for i in range(0, n_e2e, bsz))
+            one = host if (T > 1 or head) else host[0]
+            batches = ((one, np.arange(i, i + bsz, dtype=np.int64)) for i in range(0, n_e2e, bsz))
             return rank_confidence(batches, np.arange(n_e2e, dtype=np.int64), K_SELECT, measure, num_examples=n_e2e,
-                                   scorer=sc)
+                                   scorer=sc, head_kernel=head_kernel if head else None)
 
         e2e_step()
         barrier()
@@ -384,7 +419,11 @@ def main():
         if not args.no_cpu_baseline and world == 1:
             rate, cores, sample = cpu_reference_rate(w, args.cpu_seconds, dtype)
             cpu = {"value": rate / 1e9, "unit": "Gpix/s", "cores": cores, "kind": "port", "sample": sample}
-        desc = sc.describe_launch(dtype, T, chunk, H, W, C, measure)
+        if head:
+            desc = {"kernel": "score_head_kernel<%s> C=%d: tcgen05 split-TF32 UMMA 128xNx8 + TMEM epilogue" % (measure, C),
+                    "grid": 148, "block": 640, "smem_bytes": None, "stages": 4, "tile_pixels": 512}
+        else:
+            desc = sc.describe_launch(dtype, T, chunk, H, W, C, measure)
         line = {
             "metric": "pool pixels scored/s", "value": value, "unit": "Gpix/s", "n_gpus": world,
             "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": ms_step, "higher_is_better": True,

@@ -46,7 +46,7 @@ def build(force: bool = False, verbose: bool = False) -> str:
 
     def compile_one(job):
         s, o = job
-        cmd = [nvcc, *NVCC_FLAGS, "-c", s, "-o", o]
+        cmd = [nvcc, *NVCC_FLAGS, *os.environ.get("NVCC_EXTRA", "").split(), "-c", s, "-o", o]
         if verbose:
             print(" ".join(cmd), flush=True)
         r = subprocess.run(cmd, capture_output=True, text=True)

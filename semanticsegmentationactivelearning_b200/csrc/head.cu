@@ -40,6 +40,22 @@
 
 namespace als {
 
+#ifdef ALS_HEAD_TRACE
+// Bring-up instrumentation (never built into the shipped library): SM-clock timestamps of CTA 0's first tiles.
+//   [tile][0..1] splitter start/end of the tile's row, [2..3] MMA issue start/end, [4] epilogue sees the accumulator,
+//   [5] epilogue released it, [6] epilogue done, [7] producer issued the row's copy
+constexpr int kTraceTiles = 1024;
+__device__ long long g_head_trace[kTraceTiles][8];
+#define ALS_TRACE(tile, slot)                                                         \
+  do {                                                                                \
+    if (blockIdx.x == 0 && (tile) < kTraceTiles) g_head_trace[(tile)][(slot)] = clock64(); \
+  } while (0)
+#else
+#define ALS_TRACE(tile, slot) \
+  do {                        \
+  } while (0)
+#endif
+
 namespace {
 
 constexpr int kRawStages = 4;
@@ -78,6 +94,19 @@ __device__ __forceinline__ Unit decode_unit(const HeadParams& p, long long u) {
   un.valid = min(kHeadTileQuads, p.w - un.j0);
   return un;
 }
+
+__host__ __device__ constexpr int cround(int v, int m) { return (v + m - 1) / m * m; }
+__host__ __device__ constexpr int cmax(int a, int b) { return a > b ? a : b; }
+
+// Compile-time twin of head_geometry(C) (the host packs the weights with the run-time one; a static_assert-free
+// consistency check runs in plan_head).
+template <int C>
+struct Geom {
+  static constexpr int CB = cround(C, 4);
+  static constexpr int N1 = cround(2 * CB, 16), N2 = cround(2 * CB, 16), N3 = cround(CB, 16);
+  static constexpr int N0 = cmax(cround(4 * CB, 16), cmax(N1, cmax(CB + N2, CB + N3)));
+  static constexpr int ROWS = N0 + N1 + N2 + N3;
+};
 
 // TMEM -> registers, CNT consecutive columns (CNT multiple of 4, <= 32)
 template <int CNT>
@@ -134,8 +163,7 @@ __global__ void __launch_bounds__(kHeadThreads, 1) score_head_kernel(const HeadP
   unsigned char* raw_base = smem + kHeaderBytes;
   unsigned char* can_base = raw_base + kRawStages * kRawSlotBytes;
   unsigned char* w_base = can_base + kCanStages * kCanSlotBytes;
-  const int lbo_b = p.g.rows * 16;      // bytes between chunk planes of the packed weights
-  const int wpart_bytes = 4 * lbo_b;    // one precision part of the weights
+  constexpr int wpart_bytes = 4 * Geom<C>::ROWS * 16;  // one precision part of the packed weights
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -170,12 +198,14 @@ __global__ void __launch_bounds__(kHeadThreads, 1) score_head_kernel(const HeadP
       bulk_g2s(w_base, p.weights, 2u * wpart_bytes, wbar, policy);
       int s = 0;
       uint32_t ph = 0;
+      long long ptile = 0;
       for (long long u = blockIdx.x; u < p.n_units; u += gridDim.x) {
         const Unit un = decode_unit(p, u);
         const int first = un.j0 == 0 ? 1 : 0;
         for (int r = -1; r < un.rows; ++r) {
           const int row = un.i0 + r;
           mbar_wait(&empty_raw[s], ph ^ 1u);
+          if (r >= 0) { ALS_TRACE(ptile, 7); ++ptile; }
           meta[s].valid = un.valid;
           meta[s].first = first;
           meta[s].zero = row < 0 ? 1 : 0;
@@ -195,68 +225,78 @@ __global__ void __launch_bounds__(kHeadThreads, 1) score_head_kernel(const HeadP
     }
     __syncwarp();
   } else if (warp == 1) {
-    // ===== MMA issuer =====
-    if (lane == 0) {
-      uint32_t idesc[4];
-#pragma unroll
-      for (int o = 0; o < 4; ++o) idesc[o] = tc05::idesc_tf32(kHeadTileQuads, p.g.n[o]);
-      const uint32_t can_addr = smem_u32(can_base);
-      const uint32_t w_addr = smem_u32(w_base);
-      mbar_wait(wbar, 0);
-      long long seq = 0;  // canonical rows consumed so far (ring position)
-      long long tile = 0;
-      for (long long u = blockIdx.x; u < p.n_units; u += gridDim.x) {
-        const Unit un = decode_unit(p, u);
-        // halo row of the unit
-        mbar_wait(&full_can[seq % kCanStages], static_cast<uint32_t>((seq / kCanStages) & 1));
-        for (int k = 0; k < un.rows; ++k) {
-          const long long sp = seq + k, sc = seq + k + 1;
-          const int slot_prev = static_cast<int>(sp % kCanStages), slot_cur = static_cast<int>(sc % kCanStages);
-          mbar_wait(&full_can[slot_cur], static_cast<uint32_t>((sc / kCanStages) & 1));
-          const int a = static_cast<int>(tile % kAccStages);
-          mbar_wait(&empty_acc[a], static_cast<uint32_t>(((tile / kAccStages) & 1) ^ 1));
-          tc05::fence_after_sync();
+    // ===== MMA issuer: the whole warp walks the (warp-uniform) schedule, one elected lane issues =====
+    using G = Geom<C>;
+    const bool leader = tc05::elect_one();
+    constexpr uint32_t kIdesc[4] = {tc05::idesc_tf32(kHeadTileQuads, G::N0), tc05::idesc_tf32(kHeadTileQuads, G::N1),
+                                    tc05::idesc_tf32(kHeadTileQuads, G::N2), tc05::idesc_tf32(kHeadTileQuads, G::N3)};
+    constexpr uint32_t kCol0[4] = {0, 0, G::CB, G::CB};
+    constexpr uint32_t kRow0[4] = {0, G::N0, G::N0 + G::N1, G::N0 + G::N1 + G::N2};
+    constexpr uint32_t kLboB = G::ROWS * 16;         // bytes between chunk planes of the packed weights
+    constexpr uint32_t kWPart = 4 * kLboB;           // one precision part of the weights
+    const uint64_t a_base = tc05::smem_desc(smem_u32(can_base), kPlaneBytes, 128);
+    const uint64_t b_base = tc05::smem_desc(smem_u32(w_base), kLboB, 128);
+    mbar_wait(wbar, 0);
+    long long seq = 0;  // canonical rows consumed so far (ring position)
+    long long tile = 0;
+    for (long long u = blockIdx.x; u < p.n_units; u += gridDim.x) {
+      const Unit un = decode_unit(p, u);
+      // halo row of the unit
+      mbar_wait(&full_can[seq % kCanStages], static_cast<uint32_t>((seq / kCanStages) & 1));
+      for (int k = 0; k < un.rows; ++k) {
+        const long long sp = seq + k, sc = seq + k + 1;
+        const int slot_prev = static_cast<int>(sp % kCanStages), slot_cur = static_cast<int>(sc % kCanStages);
+        mbar_wait(&full_can[slot_cur], static_cast<uint32_t>((sc / kCanStages) & 1));
+        const int a = static_cast<int>(tile % kAccStages);
+        mbar_wait(&empty_acc[a], static_cast<uint32_t>(((tile / kAccStages) & 1) ^ 1));
+        tc05::fence_after_sync();
+        if (leader) {
+          ALS_TRACE(tile, 2);
           const uint32_t d = tmem + a * kAccCols;
-          bool acc = false;
-#pragma unroll
+          // descriptors differ from the base only in the 14-bit start-address field (16-byte units)
+          const uint64_t a_row[2] = {a_base + static_cast<uint32_t>(slot_cur * (kCanSlotBytes >> 4)),
+                                     a_base + static_cast<uint32_t>(slot_prev * (kCanSlotBytes >> 4))};
           // The small cross terms go first and the hi*hi products last: the tensor core truncates when it adds
           // into the accumulator, so every MMA issued after the accumulator has reached full scale costs
           // ~2^-24 of it -- 8 such steps this way round instead of 24.
+#pragma unroll
           for (int pc = 0; pc < 3; ++pc) {  // hi*lo, lo*hi, hi*hi
             const uint32_t a_part = (pc == 1) ? kPartBytes : 0;
-            const uint32_t b_part = (pc == 0) ? wpart_bytes : 0;
+            const uint32_t b_part = (pc == 0) ? kWPart : 0;
 #pragma unroll
             for (int o = 0; o < 4; ++o) {
-              const uint32_t a0 = can_addr + ((o & 1) ? slot_prev : slot_cur) * kCanSlotBytes + a_part + ((o < 2) ? 16u : 0u);
-              const uint32_t b0 = w_addr + b_part + p.g.row0[o] * 16;
 #pragma unroll
               for (int ks = 0; ks < 2; ++ks) {
-                tc05::mma_tf32(d + p.g.col0[o], tc05::smem_desc(a0 + ks * 2 * kPlaneBytes, kPlaneBytes, 128),
-                               tc05::smem_desc(b0 + ks * 2 * lbo_b, lbo_b, 128), idesc[o], acc);
-                acc = true;
+                const uint32_t a_off = (a_part + ((o < 2) ? 16u : 0u) + ks * 2 * kPlaneBytes) >> 4;
+                const uint32_t b_off = (b_part + kRow0[o] * 16 + ks * 2 * kLboB) >> 4;
+                tc05::mma_tf32(d + kCol0[o], a_row[o & 1] + a_off, b_base + b_off, kIdesc[o],
+                               !(pc == 0 && o == 0 && ks == 0));
               }
             }
           }
           tc05::commit(&full_acc[a]);
           tc05::commit(&empty_can[slot_prev]);
           if (k == un.rows - 1) tc05::commit(&empty_can[slot_cur]);
-          ++tile;
+          ALS_TRACE(tile, 3);
         }
-        seq += un.rows + 1;
+        __syncwarp();
+        ++tile;
       }
+      seq += un.rows + 1;
     }
-    __syncwarp();
   } else if (warp < kFirstEpilogueWarp) {
     // ===== splitters: raw NHWC row -> canonical hi / lo operand planes =====
     const int st = threadIdx.x - 64;
     int s = 0, c = 0;
     uint32_t phs = 0, phc = 0;
+    long long stile = 0;
     for (long long u = blockIdx.x; u < p.n_units; u += gridDim.x) {
       const Unit un = decode_unit(p, u);
       for (int r = -1; r < un.rows; ++r) {
         mbar_wait(&full_raw[s], phs);
         const RawMeta m = meta[s];
         mbar_wait(&empty_can[c], phc ^ 1u);
+        if (r >= 0 && st == 0) ALS_TRACE(stile, 0);
         const unsigned char* raw = raw_base + s * kRawSlotBytes;
         unsigned char* hi = can_base + c * kCanSlotBytes;
         const int lo_px = m.first ? 1 : 0;
@@ -278,6 +318,10 @@ __global__ void __launch_bounds__(kHeadThreads, 1) score_head_kernel(const HeadP
         if (lane == 0) {
           mbar_arrive(&full_can[c]);
           mbar_arrive(&empty_raw[s]);
+        }
+        if (r >= 0) {
+          if (st == 0) ALS_TRACE(stile, 1);
+          ++stile;
         }
         if (++s == kRawStages) { s = 0; phs ^= 1u; }
         if (++c == kCanStages) { c = 0; phc ^= 1u; }
@@ -305,6 +349,7 @@ __global__ void __launch_bounds__(kHeadThreads, 1) score_head_kernel(const HeadP
         if ((tile % kAccStages) != a) continue;
         mbar_wait(&full_acc[a], static_cast<uint32_t>((tile / kAccStages) & 1));
         tc05::fence_after_sync();
+        if (quarter == 0 && lane == 0) ALS_TRACE(tile, 4);
         float conf[4];
         int lbl[4];
 #pragma unroll
@@ -316,6 +361,7 @@ __global__ void __launch_bounds__(kHeadThreads, 1) score_head_kernel(const HeadP
             tc05::fence_before_sync();
             __syncwarp();
             if (lane == 0) mbar_arrive(&empty_acc[a]);
+            if (quarter == 0 && lane == 0) ALS_TRACE(tile, 5);
           }
           float x[C];
 #pragma unroll
@@ -327,6 +373,7 @@ __global__ void __launch_bounds__(kHeadThreads, 1) score_head_kernel(const HeadP
               conf[b] = conf_single<C, 1, true, MEASURE, true>(x, C, sp);
           }
         }
+        if (quarter == 0 && lane == 0) ALS_TRACE(tile, 6);
         if (valid) {
 #pragma unroll
           for (int b = 0; b < 4; ++b) acc.add(conf[b], sp.fx_scale);
@@ -437,8 +484,23 @@ HeadPlan plan_head(int C, int measure, int num_sms) {
   plan.block = kHeadThreads;
   plan.grid = num_sms;
   plan.smem_bytes = kHeaderBytes + kRawStages * kRawSlotBytes + kCanStages * kCanSlotBytes + 2 * 4 * g.rows * 16;
+  auto agrees = [&](int cb, int n0, int n1, int n2, int n3, int rows) {
+    return g.CB == cb && g.n[0] == n0 && g.n[1] == n1 && g.n[2] == n2 && g.n[3] == n3 && g.rows == rows && g.col0[0] == 0 &&
+           g.col0[1] == 0 && g.col0[2] == cb && g.col0[3] == cb && g.row0[1] == n0 && g.row0[2] == n0 + n1 &&
+           g.row0[3] == n0 + n1 + n2;
+  };
+  const bool same = (C == 6) ? agrees(Geom<6>::CB, Geom<6>::N0, Geom<6>::N1, Geom<6>::N2, Geom<6>::N3, Geom<6>::ROWS)
+                             : agrees(Geom<19>::CB, Geom<19>::N0, Geom<19>::N1, Geom<19>::N2, Geom<19>::N3, Geom<19>::ROWS);
+  if (!same) plan.func = nullptr;  // host packing and device geometry disagree: refuse rather than mis-compute
   return plan;
 }
+
+#ifdef ALS_HEAD_TRACE
+extern "C" __attribute__((visibility("default"))) int als_debug_head_trace(long long* out, int tiles) {
+  if (tiles > kTraceTiles) tiles = kTraceTiles;
+  return cudaMemcpyFromSymbol(out, g_head_trace, sizeof(long long) * 8 * tiles) == cudaSuccess ? tiles : -1;
+}
+#endif
 
 cudaError_t launch_head(const HeadPlan& plan, HeadParams p, cudaStream_t stream) {
   if (p.n_units <= 0) return cudaSuccess;
