@@ -21,14 +21,18 @@
 // fp32: hi*lo + lo*hi + hi*hi (the dropped lo*lo term and the tf32 rounding of the lo parts are ~2^-24 relative each).
 //
 // Data movement.  One 1-D bulk copy (TMA engine, UBLKCP) per feature row segment of 129 pixels (one halo
-// pixel on the left) into a raw ring; two "splitter" warps rewrite it as the canonical K-major no-swizzle
-// UMMA operand (16-byte chunk planes, see tc05.cuh), hi and lo, where a matrix shifted by one pixel is the
-// same buffer + 16 bytes -- so the (j-1) operands need no second copy.  A CTA walks down a strip of 128
-// columns: each feature row is loaded once and used by two consecutive tiles (as row i, then as row i-1).
+// pixel on the left) into a raw ring in shared memory.  Four "loader" warps transpose it into 16-byte chunk
+// planes (so that a thread can read ITS pixel without bank conflicts: in NHWC a pixel is 64 B, half a bank
+// row), split every value into hi/lo in registers and write the A operands into TENSOR MEMORY with
+// tcgen05.st (lane = pixel, 16 columns = channels): own pixel and left neighbour, hi and lo = 64 columns per
+// feature row, a ring of three rows.  The MMAs take A from tensor memory and only the (small) weight
+// operand from shared memory -- with A in shared memory every one of the 24 MMAs of a tile re-read a 4 KB
+// A tile and the kernel was shared-memory bound at ~1000 clk / tile (profiles/r01_head_*).  A CTA walks
+// down a strip of 128 columns: each feature row is loaded once and used by two consecutive tiles.
 //
-// Roles (640 threads, 1 CTA / SM, persistent, static round-robin over units of R rows x 128 columns):
-//   warp 0      producer: bulk copies                  warp 1      MMA issuer (one lane), TMEM owner
-//   warps 2-3   splitters: raw -> hi/lo operands       warps 4-19  epilogue: 4 accumulator stages x 4 lane quarters
+// Roles (576 threads, 1 CTA / SM, persistent, static round-robin over units of R rows x 128 columns):
+//   warp 0      producer: bulk copies                  warp 1       MMA issuer (one elected lane), TMEM owner
+//   warps 2-5   loaders: raw -> hi/lo A rows in TMEM   warps 6-17   epilogue: 3 accumulator stages x 4 lane quarters
 #include "head.cuh"
 
 #include <math.h>
@@ -58,18 +62,20 @@ __device__ long long g_head_trace[kTraceTiles][8];
 
 namespace {
 
-constexpr int kRawStages = 4;
-constexpr int kCanStages = 4;
-constexpr int kAccStages = 4;
-constexpr int kAccCols = 128;                         // TMEM columns per accumulator stage
+constexpr int kRawStages = 6;
+constexpr int kARing = 3;                             // feature rows resident in tensor memory
+constexpr int kARowCols = 64;                         // [own hi 16 | own lo 16 | left hi 16 | left lo 16]
+constexpr int kAccStages = 3;
+constexpr int kTmemCols = 512;
 constexpr int kSlotPx = kHeadTileQuads + 1;           // 129 pixels: one halo pixel on the left
 constexpr int kRawSlotBytes = 8320;                   // 129 * 64 rounded up to 128
-constexpr int kPlaneBytes = (kSlotPx + 1) * 16;       // 2080: stride between 16-byte chunk planes (LBO of A)
-constexpr int kPartBytes = 4 * kPlaneBytes;           // 8320: one precision part (hi or lo) of a row
-constexpr int kCanSlotBytes = 2 * kPartBytes;         // 16640
-constexpr int kHeadThreads = 640;
+constexpr int kPlaneBytes = (kSlotPx + 1) * 16;       // 2080: stride between the 16-byte chunk planes of the transposed row
+constexpr int kCanBytes = 4 * kPlaneBytes;            // 8320: one transposed row
+constexpr int kFirstLoaderWarp = 2;
+constexpr int kLoaderThreads = 128;
+constexpr int kFirstEpilogueWarp = 6;
+constexpr int kHeadThreads = 32 * (kFirstEpilogueWarp + 4 * kAccStages);  // 576
 constexpr int kHeaderBytes = 512;
-constexpr int kFirstEpilogueWarp = 4;
 
 struct RawMeta {
   int valid;  // quad columns of this strip that exist (<= 128)
@@ -147,23 +153,48 @@ __device__ __forceinline__ void ld_cols(uint32_t taddr, float (&v)[CNT]) {
 
 }  // namespace
 
+// fp32 -> tf32 with round-to-nearest (ties away) in integer arithmetic; the tensor core itself TRUNCATES its
+// fp32 inputs to tf32 (probes/umma_probe.cu), so the rounding has to happen here.
+__device__ __forceinline__ uint32_t rna_tf32_bits(float x) { return (__float_as_uint(x) + 0x1000u) & 0xffffe000u; }
+
+// one pixel (16 channels as 4 float4) -> hi and lo parts -> 2 x 16 tensor-memory columns of this thread's lane
+__device__ __forceinline__ void store_split(uint32_t taddr, const float4 (&v)[4]) {
+  uint32_t hi[16], lo[16];
+#pragma unroll
+  for (int c = 0; c < 4; ++c) {
+    const float x[4] = {v[c].x, v[c].y, v[c].z, v[c].w};
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      hi[4 * c + j] = rna_tf32_bits(x[j]);
+      lo[4 * c + j] = rna_tf32_bits(x[j] - __uint_as_float(hi[4 * c + j]));
+    }
+  }
+  tc05::st16(taddr, hi);
+  tc05::st16(taddr + 16, lo);
+}
+
 template <int C, int MEASURE>
 __global__ void __launch_bounds__(kHeadThreads, 1) score_head_kernel(const HeadParams p) {
-  constexpr int CB = (C + 3) & ~3;
+  using G = Geom<C>;
+  constexpr int CB = G::CB;
+  constexpr int kAccStride = G::N0;                                  // accumulator columns per stage
+  constexpr int kACol0 = (kAccStages * kAccStride + 31) / 32 * 32;  // first column of the A-row ring
+  static_assert(kACol0 + kARing * kARowCols <= kTmemCols, "tensor memory budget");
+  constexpr int wpart_bytes = 4 * G::ROWS * 16;  // one precision part of the packed weights
+
   extern __shared__ __align__(128) unsigned char smem[];
   uint64_t* full_raw = reinterpret_cast<uint64_t*>(smem);
   uint64_t* empty_raw = full_raw + kRawStages;
-  uint64_t* full_can = empty_raw + kRawStages;
-  uint64_t* empty_can = full_can + kCanStages;
-  uint64_t* full_acc = empty_can + kCanStages;
+  uint64_t* full_a = empty_raw + kRawStages;
+  uint64_t* empty_a = full_a + kARing;
+  uint64_t* full_acc = empty_a + kARing;
   uint64_t* empty_acc = full_acc + kAccStages;
   uint64_t* wbar = empty_acc + kAccStages;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + 256);
   RawMeta* meta = reinterpret_cast<RawMeta*>(smem + 320);
   unsigned char* raw_base = smem + kHeaderBytes;
-  unsigned char* can_base = raw_base + kRawStages * kRawSlotBytes;
-  unsigned char* w_base = can_base + kCanStages * kCanSlotBytes;
-  constexpr int wpart_bytes = 4 * Geom<C>::ROWS * 16;  // one precision part of the packed weights
+  unsigned char* can = raw_base + kRawStages * kRawSlotBytes;
+  unsigned char* w_base = can + kCanBytes;
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -171,11 +202,11 @@ __global__ void __launch_bounds__(kHeadThreads, 1) score_head_kernel(const HeadP
   if (threadIdx.x == 0) {
     for (int s = 0; s < kRawStages; ++s) {
       mbar_init(&full_raw[s], 1);
-      mbar_init(&empty_raw[s], 2);
+      mbar_init(&empty_raw[s], kLoaderThreads / 32);
     }
-    for (int s = 0; s < kCanStages; ++s) {
-      mbar_init(&full_can[s], 2);
-      mbar_init(&empty_can[s], 1);
+    for (int s = 0; s < kARing; ++s) {
+      mbar_init(&full_a[s], kLoaderThreads / 32);
+      mbar_init(&empty_a[s], 1);
     }
     for (int s = 0; s < kAccStages; ++s) {
       mbar_init(&full_acc[s], 1);
@@ -184,7 +215,7 @@ __global__ void __launch_bounds__(kHeadThreads, 1) score_head_kernel(const HeadP
     mbar_init(wbar, 1);
     fence_mbar_init();
   }
-  if (warp == 1) tc05::tmem_alloc<kAccStages * kAccCols>(tmem_slot);
+  if (warp == 1) tc05::tmem_alloc<kTmemCols>(tmem_slot);
   tc05::fence_before_sync();
   __syncthreads();
   tc05::fence_after_sync();
@@ -226,7 +257,6 @@ __global__ void __launch_bounds__(kHeadThreads, 1) score_head_kernel(const HeadP
     __syncwarp();
   } else if (warp == 1) {
     // ===== MMA issuer: the whole warp walks the (warp-uniform) schedule, one elected lane issues =====
-    using G = Geom<C>;
     const bool leader = tc05::elect_one();
     constexpr uint32_t kIdesc[4] = {tc05::idesc_tf32(kHeadTileQuads, G::N0), tc05::idesc_tf32(kHeadTileQuads, G::N1),
                                     tc05::idesc_tf32(kHeadTileQuads, G::N2), tc05::idesc_tf32(kHeadTileQuads, G::N3)};
@@ -234,49 +264,46 @@ __global__ void __launch_bounds__(kHeadThreads, 1) score_head_kernel(const HeadP
     constexpr uint32_t kRow0[4] = {0, G::N0, G::N0 + G::N1, G::N0 + G::N1 + G::N2};
     constexpr uint32_t kLboB = G::ROWS * 16;         // bytes between chunk planes of the packed weights
     constexpr uint32_t kWPart = 4 * kLboB;           // one precision part of the weights
-    const uint64_t a_base = tc05::smem_desc(smem_u32(can_base), kPlaneBytes, 128);
     const uint64_t b_base = tc05::smem_desc(smem_u32(w_base), kLboB, 128);
     mbar_wait(wbar, 0);
-    long long seq = 0;  // canonical rows consumed so far (ring position)
+    long long seq = 0;  // feature rows consumed so far (position in the A-row ring)
     long long tile = 0;
     for (long long u = blockIdx.x; u < p.n_units; u += gridDim.x) {
       const Unit un = decode_unit(p, u);
       // halo row of the unit
-      mbar_wait(&full_can[seq % kCanStages], static_cast<uint32_t>((seq / kCanStages) & 1));
+      mbar_wait(&full_a[seq % kARing], static_cast<uint32_t>((seq / kARing) & 1));
       for (int k = 0; k < un.rows; ++k) {
         const long long sp = seq + k, sc = seq + k + 1;
-        const int slot_prev = static_cast<int>(sp % kCanStages), slot_cur = static_cast<int>(sc % kCanStages);
-        mbar_wait(&full_can[slot_cur], static_cast<uint32_t>((sc / kCanStages) & 1));
+        const int rb_prev = static_cast<int>(sp % kARing), rb_cur = static_cast<int>(sc % kARing);
+        mbar_wait(&full_a[rb_cur], static_cast<uint32_t>((sc / kARing) & 1));
         const int a = static_cast<int>(tile % kAccStages);
         mbar_wait(&empty_acc[a], static_cast<uint32_t>(((tile / kAccStages) & 1) ^ 1));
         tc05::fence_after_sync();
         if (leader) {
           ALS_TRACE(tile, 2);
-          const uint32_t d = tmem + a * kAccCols;
-          // descriptors differ from the base only in the 14-bit start-address field (16-byte units)
-          const uint64_t a_row[2] = {a_base + static_cast<uint32_t>(slot_cur * (kCanSlotBytes >> 4)),
-                                     a_base + static_cast<uint32_t>(slot_prev * (kCanSlotBytes >> 4))};
+          const uint32_t d = tmem + a * kAccStride;
+          const uint32_t a_row[2] = {tmem + kACol0 + rb_cur * kARowCols, tmem + kACol0 + rb_prev * kARowCols};
           // The small cross terms go first and the hi*hi products last: the tensor core truncates when it adds
           // into the accumulator, so every MMA issued after the accumulator has reached full scale costs
           // ~2^-24 of it -- 8 such steps this way round instead of 24.
 #pragma unroll
           for (int pc = 0; pc < 3; ++pc) {  // hi*lo, lo*hi, hi*hi
-            const uint32_t a_part = (pc == 1) ? kPartBytes : 0;
+            const uint32_t a_part = (pc == 1) ? 16 : 0;        // columns: hi 0..15, lo 16..31
             const uint32_t b_part = (pc == 0) ? kWPart : 0;
 #pragma unroll
             for (int o = 0; o < 4; ++o) {
 #pragma unroll
               for (int ks = 0; ks < 2; ++ks) {
-                const uint32_t a_off = (a_part + ((o < 2) ? 16u : 0u) + ks * 2 * kPlaneBytes) >> 4;
+                const uint32_t a_col = ((o < 2) ? 0u : 32u) + a_part + ks * 8;  // own pixel for sources (.,j), left for (.,j-1)
                 const uint32_t b_off = (b_part + kRow0[o] * 16 + ks * 2 * kLboB) >> 4;
-                tc05::mma_tf32(d + kCol0[o], a_row[o & 1] + a_off, b_base + b_off, kIdesc[o],
-                               !(pc == 0 && o == 0 && ks == 0));
+                tc05::mma_tf32_ts(d + kCol0[o], a_row[o & 1] + a_col, b_base + b_off, kIdesc[o],
+                                  !(pc == 0 && o == 0 && ks == 0));
               }
             }
           }
           tc05::commit(&full_acc[a]);
-          tc05::commit(&empty_can[slot_prev]);
-          if (k == un.rows - 1) tc05::commit(&empty_can[slot_cur]);
+          tc05::commit(&empty_a[rb_prev]);
+          if (k == un.rows - 1) tc05::commit(&empty_a[rb_cur]);
           ALS_TRACE(tile, 3);
         }
         __syncwarp();
@@ -285,55 +312,63 @@ __global__ void __launch_bounds__(kHeadThreads, 1) score_head_kernel(const HeadP
       seq += un.rows + 1;
     }
   } else if (warp < kFirstEpilogueWarp) {
-    // ===== splitters: raw NHWC row -> canonical hi / lo operand planes =====
-    const int st = threadIdx.x - 64;
-    int s = 0, c = 0;
-    uint32_t phs = 0, phc = 0;
+    // ===== loaders: raw NHWC row -> chunk planes (shared) -> hi / lo A rows in tensor memory =====
+    const int lt = threadIdx.x - 32 * kFirstLoaderWarp;  // 0..127
+    const int quarter = warp & 3;                        // TMEM lane quarter this warp may write
+    const int m = quarter * 32 + lane;                   // A row = accumulator row = quad column inside the strip
+    const uint32_t t_lane = tmem + (static_cast<uint32_t>(quarter * 32) << 16) + kACol0;
+    int s = 0, rb = 0;
+    uint32_t phs = 0, pha = 0;
     long long stile = 0;
     for (long long u = blockIdx.x; u < p.n_units; u += gridDim.x) {
       const Unit un = decode_unit(p, u);
       for (int r = -1; r < un.rows; ++r) {
         mbar_wait(&full_raw[s], phs);
-        const RawMeta m = meta[s];
-        mbar_wait(&empty_can[c], phc ^ 1u);
-        if (r >= 0 && st == 0) ALS_TRACE(stile, 0);
+        const RawMeta mt = meta[s];
+        if (r >= 0 && lt == 0) ALS_TRACE(stile, 0);
+        // (a) transpose: 16-byte chunk q of the raw row -> plane (q & 3), pixel (q >> 2).  Both sides conflict free.
+        asm volatile("bar.sync 1, %0;" ::"n"(kLoaderThreads) : "memory");  // the previous row has been read out of `can`
         const unsigned char* raw = raw_base + s * kRawSlotBytes;
-        unsigned char* hi = can_base + c * kCanSlotBytes;
-        const int lo_px = m.first ? 1 : 0;
-#pragma unroll 3
-        for (int q = st; q < kSlotPx * 4; q += 64) {
+        const int lo_px = mt.first ? 1 : 0;
+#pragma unroll
+        for (int q = lt; q < kSlotPx * 4; q += kLoaderThreads) {
           const int px = q >> 2, ch = q & 3;
           float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-          if (!m.zero && px >= lo_px && px <= m.valid) v = *reinterpret_cast<const float4*>(raw + q * 16);
-          float4 vh, vl;
-          vh.x = tc05::round_tf32(v.x); vh.y = tc05::round_tf32(v.y); vh.z = tc05::round_tf32(v.z); vh.w = tc05::round_tf32(v.w);
-          vl.x = tc05::round_tf32(v.x - vh.x); vl.y = tc05::round_tf32(v.y - vh.y);
-          vl.z = tc05::round_tf32(v.z - vh.z); vl.w = tc05::round_tf32(v.w - vh.w);
-          unsigned char* dst = hi + ch * kPlaneBytes + px * 16;
-          *reinterpret_cast<float4*>(dst) = vh;
-          *reinterpret_cast<float4*>(dst + kPartBytes) = vl;
+          if (!mt.zero && px >= lo_px && px <= mt.valid) v = *reinterpret_cast<const float4*>(raw + q * 16);
+          *reinterpret_cast<float4*>(can + ch * kPlaneBytes + px * 16) = v;
         }
-        tc05::fence_proxy_async();
+        asm volatile("bar.sync 1, %0;" ::"n"(kLoaderThreads) : "memory");
+        if (lane == 0) mbar_arrive(&empty_raw[s]);
+        // (b) this thread's pixel (slot pixel m + 1) and its left neighbour (slot pixel m) -> tensor memory
+        mbar_wait(&empty_a[rb], pha ^ 1u);  // the MMAs that read this ring slot have completed
+        tc05::fence_after_sync();
+        const uint32_t t_row = t_lane + rb * kARowCols;
+        float4 v[4];
+#pragma unroll
+        for (int c = 0; c < 4; ++c) v[c] = *reinterpret_cast<const float4*>(can + c * kPlaneBytes + (m + 1) * 16);
+        store_split(t_row, v);
+#pragma unroll
+        for (int c = 0; c < 4; ++c) v[c] = *reinterpret_cast<const float4*>(can + c * kPlaneBytes + m * 16);
+        store_split(t_row + 32, v);
+        tc05::st_wait();
+        tc05::fence_before_sync();
         __syncwarp();
-        if (lane == 0) {
-          mbar_arrive(&full_can[c]);
-          mbar_arrive(&empty_raw[s]);
-        }
+        if (lane == 0) mbar_arrive(&full_a[rb]);
         if (r >= 0) {
-          if (st == 0) ALS_TRACE(stile, 1);
+          if (lt == 0) ALS_TRACE(stile, 1);
           ++stile;
         }
         if (++s == kRawStages) { s = 0; phs ^= 1u; }
-        if (++c == kCanStages) { c = 0; phc ^= 1u; }
+        if (++rb == kARing) { rb = 0; pha ^= 1u; }
       }
     }
   } else {
     // ===== epilogue: tensor memory -> confidences -> per-image sums =====
     const int e = warp - kFirstEpilogueWarp;
-    const int a = e >> 2;        // accumulator stage this warp serves
+    const int a = e >> 2;          // accumulator stage this warp serves
     const int quarter = warp & 3;  // TMEM lane quarter this warp may read
     const int m = quarter * 32 + lane;
-    const uint32_t tbase = tmem + (static_cast<uint32_t>(quarter * 32) << 16) + a * kAccCols;
+    const uint32_t tbase = tmem + (static_cast<uint32_t>(quarter * 32) << 16) + a * kAccStride;
     const ScoreParams& sp = p.sp;
     const int W = 2 * p.w;
     ImageAcc acc;
@@ -396,7 +431,7 @@ __global__ void __launch_bounds__(kHeadThreads, 1) score_head_kernel(const HeadP
 
   tc05::fence_before_sync();
   __syncthreads();
-  if (warp == 1) tc05::tmem_dealloc<kAccStages * kAccCols>(tmem);
+  if (warp == 1) tc05::tmem_dealloc<kTmemCols>(tmem);
 }
 
 // ---- host side -------------------------------------------------------------------------------------
@@ -483,7 +518,7 @@ HeadPlan plan_head(int C, int measure, int num_sms) {
   const HeadGeom g = head_geometry(C);
   plan.block = kHeadThreads;
   plan.grid = num_sms;
-  plan.smem_bytes = kHeaderBytes + kRawStages * kRawSlotBytes + kCanStages * kCanSlotBytes + 2 * 4 * g.rows * 16;
+  plan.smem_bytes = kHeaderBytes + kRawStages * kRawSlotBytes + kCanBytes + 2 * 4 * g.rows * 16;
   auto agrees = [&](int cb, int n0, int n1, int n2, int n3, int rows) {
     return g.CB == cb && g.n[0] == n0 && g.n[1] == n1 && g.n[2] == n2 && g.n[3] == n3 && g.rows == rows && g.col0[0] == 0 &&
            g.col0[1] == 0 && g.col0[2] == cb && g.col0[3] == cb && g.row0[1] == n0 && g.row0[2] == n0 + n1 &&
