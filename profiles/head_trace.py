@@ -22,7 +22,7 @@ t0 = buf[0, 7]
 b = buf - t0
 names = ["split0", "split1", "mma0", "mma1", "acc_full", "acc_rel", "epi_done", "copy"]
 print("tile " + " ".join("%9s" % x for x in names))
-for i in list(range(0, 12)) + list(range(200, 216)):
+for i in list(range(0, 6)) + list(range(200, 212)):
     print("%4d " % i + " ".join("%9d" % v for v in b[i]))
 d = np.diff(buf[100:900], axis=0)
 print("steady-state period per tile (clks), median by column:", dict(zip(names, np.median(d, axis=0).astype(int).tolist())))

@@ -17,7 +17,7 @@
 // 16) instead of one 64 x 4C GEMM that is 44 % zeros.
 //
 // Precision.  kind::tf32 keeps 11 significand bits, the parity bar is 1e-5 on confidences, so both
-// operands are split x = hi + lo (hi = tf32(x), lo = tf32(x - hi)) and three products are accumulated in
+// operands are split x = hi + lo (hi = x rounded to tf32, lo = x - hi) and three products are accumulated in
 // fp32: hi*lo + lo*hi + hi*hi (the dropped lo*lo term and the tf32 rounding of the lo parts are ~2^-24 relative each).
 //
 // Data movement.  One 1-D bulk copy (TMA engine, UBLKCP) per feature row segment of 129 pixels (one halo
@@ -30,9 +30,10 @@
 // A tile and the kernel was shared-memory bound at ~1000 clk / tile (profiles/r01_head_*).  A CTA walks
 // down a strip of 128 columns: each feature row is loaded once and used by two consecutive tiles.
 //
-// Roles (576 threads, 1 CTA / SM, persistent, static round-robin over units of R rows x 128 columns):
-//   warp 0      producer: bulk copies                  warp 1       MMA issuer (one elected lane), TMEM owner
-//   warps 2-5   loaders: raw -> hi/lo A rows in TMEM   warps 6-17   epilogue: 3 accumulator stages x 4 lane quarters
+// Roles (704 threads, 1 CTA / SM, persistent, static round-robin over units of R rows x 128 columns):
+//   warps 0-11  epilogue: 3 accumulator stages x 4 lane quarters
+//   warps 12-19 loaders: raw -> hi/lo A rows in TMEM (two groups of four warps, alternate rows)
+//   warp 20     MMA issuer (one elected lane), TMEM owner      warp 21  producer: bulk copies
 #include "head.cuh"
 
 #include <math.h>
@@ -63,7 +64,7 @@ __device__ long long g_head_trace[kTraceTiles][8];
 namespace {
 
 constexpr int kRawStages = 6;
-constexpr int kARing = 3;                             // feature rows resident in tensor memory
+constexpr int kARing = 4;                             // feature rows resident in tensor memory (2 in use by the MMAs, 2 being written)
 constexpr int kARowCols = 64;                         // [own hi 16 | own lo 16 | left hi 16 | left lo 16]
 constexpr int kAccStages = 3;
 constexpr int kTmemCols = 512;
@@ -71,10 +72,15 @@ constexpr int kSlotPx = kHeadTileQuads + 1;           // 129 pixels: one halo pi
 constexpr int kRawSlotBytes = 8320;                   // 129 * 64 rounded up to 128
 constexpr int kPlaneBytes = (kSlotPx + 1) * 16;       // 2080: stride between the 16-byte chunk planes of the transposed row
 constexpr int kCanBytes = 4 * kPlaneBytes;            // 8320: one transposed row
-constexpr int kFirstLoaderWarp = 2;
-constexpr int kLoaderThreads = 128;
-constexpr int kFirstEpilogueWarp = 6;
-constexpr int kHeadThreads = 32 * (kFirstEpilogueWarp + 4 * kAccStages);  // 576
+// Warp roles by warp id.  The SM's issue arbiter favours HIGHER warp ids, so the roles on the critical path
+// (producer, MMA issuer, loaders) sit above the twelve epilogue warps, which mostly wait.
+constexpr int kLoaderGroups = 2;                      // two groups of four warps take alternate feature rows
+constexpr int kLoaderThreads = 128;                   // per group
+constexpr int kFirstEpilogueWarp = 0;                 // warps 0..11: stage = warp >> 2, lane quarter = warp & 3
+constexpr int kFirstLoaderWarp = 4 * kAccStages;      // warps 12..19
+constexpr int kMmaWarp = kFirstLoaderWarp + 4 * kLoaderGroups;  // 20
+constexpr int kProducerWarp = kMmaWarp + 1;           // 21
+constexpr int kHeadThreads = 32 * (kProducerWarp + 1);  // 704
 constexpr int kHeaderBytes = 512;
 
 struct RawMeta {
@@ -153,20 +159,30 @@ __device__ __forceinline__ void ld_cols(uint32_t taddr, float (&v)[CNT]) {
 
 }  // namespace
 
-// fp32 -> tf32 with round-to-nearest (ties away) in integer arithmetic; the tensor core itself TRUNCATES its
-// fp32 inputs to tf32 (probes/umma_probe.cu), so the rounding has to happen here.
-__device__ __forceinline__ uint32_t rna_tf32_bits(float x) { return (__float_as_uint(x) + 0x1000u) & 0xffffe000u; }
-
-// one pixel (16 channels as 4 float4) -> hi and lo parts -> 2 x 16 tensor-memory columns of this thread's lane
+// one pixel (16 channels as 4 float4) -> hi and lo parts -> 2 x 16 tensor-memory columns of this thread's lane.
+// The tensor core TRUNCATES its fp32 inputs to tf32 (probes/umma_probe.cu), so hi must be rounded here:
+// Veltkamp's split with 2^13 + 1 gives hi = x rounded to nearest on 11 significand bits and lo = x - hi exactly,
+// two packed FMA-pipe instructions per element pair each.  lo (|lo| <= 2^-11 |x|) is left to the hardware's
+// truncation: an error of at most 2^-21 |x|, the same order as the dropped lo*lo term.
 __device__ __forceinline__ void store_split(uint32_t taddr, const float4 (&v)[4]) {
+  const f32x2 k2 = pack2(8193.0f, 8193.0f), m1 = pack2(-1.0f, -1.0f);
   uint32_t hi[16], lo[16];
 #pragma unroll
   for (int c = 0; c < 4; ++c) {
-    const float x[4] = {v[c].x, v[c].y, v[c].z, v[c].w};
+    const f32x2 x2[2] = {pack2(v[c].x, v[c].y), pack2(v[c].z, v[c].w)};
 #pragma unroll
-    for (int j = 0; j < 4; ++j) {
-      hi[4 * c + j] = rna_tf32_bits(x[j]);
-      lo[4 * c + j] = rna_tf32_bits(x[j] - __uint_as_float(hi[4 * c + j]));
+    for (int j = 0; j < 2; ++j) {
+      const f32x2 cc = fma2(x2[j], k2, pack2(0.f, 0.f));  // c = x * (2^13 + 1)
+      const f32x2 t = fma2(x2[j], m1, cc);                 // c - x
+      const f32x2 h = fma2(t, m1, cc);                     // hi = c - (c - x)
+      const f32x2 l = fma2(h, m1, x2[j]);                  // lo = x - hi
+      float a0, a1;
+      unpack2(h, a0, a1);
+      hi[4 * c + 2 * j] = __float_as_uint(a0);
+      hi[4 * c + 2 * j + 1] = __float_as_uint(a1);
+      unpack2(l, a0, a1);
+      lo[4 * c + 2 * j] = __float_as_uint(a0);
+      lo[4 * c + 2 * j + 1] = __float_as_uint(a1);
     }
   }
   tc05::st16(taddr, hi);
@@ -194,7 +210,7 @@ __global__ void __launch_bounds__(kHeadThreads, 1) score_head_kernel(const HeadP
   RawMeta* meta = reinterpret_cast<RawMeta*>(smem + 320);
   unsigned char* raw_base = smem + kHeaderBytes;
   unsigned char* can = raw_base + kRawStages * kRawSlotBytes;
-  unsigned char* w_base = can + kCanBytes;
+  unsigned char* w_base = can + kLoaderGroups * kCanBytes;
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -215,13 +231,13 @@ __global__ void __launch_bounds__(kHeadThreads, 1) score_head_kernel(const HeadP
     mbar_init(wbar, 1);
     fence_mbar_init();
   }
-  if (warp == 1) tc05::tmem_alloc<kTmemCols>(tmem_slot);
+  if (warp == kMmaWarp) tc05::tmem_alloc<kTmemCols>(tmem_slot);
   tc05::fence_before_sync();
   __syncthreads();
   tc05::fence_after_sync();
   const uint32_t tmem = *tmem_slot;
 
-  if (warp == 0) {
+  if (warp == kProducerWarp) {
     // ===== producer =====
     if (lane == 0) {
       const uint64_t policy = l2_policy_evict_first();
@@ -235,7 +251,7 @@ __global__ void __launch_bounds__(kHeadThreads, 1) score_head_kernel(const HeadP
         const int first = un.j0 == 0 ? 1 : 0;
         for (int r = -1; r < un.rows; ++r) {
           const int row = un.i0 + r;
-          mbar_wait(&empty_raw[s], ph ^ 1u);
+          mbar_wait_relaxed(&empty_raw[s], ph ^ 1u);
           if (r >= 0) { ALS_TRACE(ptile, 7); ++ptile; }
           meta[s].valid = un.valid;
           meta[s].first = first;
@@ -255,7 +271,7 @@ __global__ void __launch_bounds__(kHeadThreads, 1) score_head_kernel(const HeadP
       }
     }
     __syncwarp();
-  } else if (warp == 1) {
+  } else if (warp == kMmaWarp) {
     // ===== MMA issuer: the whole warp walks the (warp-uniform) schedule, one elected lane issues =====
     const bool leader = tc05::elect_one();
     constexpr uint32_t kIdesc[4] = {tc05::idesc_tf32(kHeadTileQuads, G::N0), tc05::idesc_tf32(kHeadTileQuads, G::N1),
@@ -311,55 +327,60 @@ __global__ void __launch_bounds__(kHeadThreads, 1) score_head_kernel(const HeadP
       }
       seq += un.rows + 1;
     }
-  } else if (warp < kFirstEpilogueWarp) {
+  } else if (warp >= kFirstLoaderWarp) {
     // ===== loaders: raw NHWC row -> chunk planes (shared) -> hi / lo A rows in tensor memory =====
-    const int lt = threadIdx.x - 32 * kFirstLoaderWarp;  // 0..127
+    const int grp = (warp - kFirstLoaderWarp) >> 2;      // rows alternate between the two groups
+    const int lt = threadIdx.x - 32 * kFirstLoaderWarp - grp * kLoaderThreads;  // 0..127 inside the group
     const int quarter = warp & 3;                        // TMEM lane quarter this warp may write
     const int m = quarter * 32 + lane;                   // A row = accumulator row = quad column inside the strip
     const uint32_t t_lane = tmem + (static_cast<uint32_t>(quarter * 32) << 16) + kACol0;
-    int s = 0, rb = 0;
-    uint32_t phs = 0, pha = 0;
+    unsigned char* can_g = can + grp * kCanBytes;
+    long long rs = 0;     // feature rows seen so far (ring positions are derived from it)
     long long stile = 0;
     for (long long u = blockIdx.x; u < p.n_units; u += gridDim.x) {
       const Unit un = decode_unit(p, u);
-      for (int r = -1; r < un.rows; ++r) {
-        mbar_wait(&full_raw[s], phs);
+      for (int r = -1; r < un.rows; ++r, ++rs) {
+        if (r >= 0) ++stile;
+        if ((rs & 1) != grp) continue;
+        const int s = static_cast<int>(rs % kRawStages), rb = static_cast<int>(rs % kARing);
+        mbar_wait(&full_raw[s], static_cast<uint32_t>((rs / kRawStages) & 1));
         const RawMeta mt = meta[s];
-        if (r >= 0 && lt == 0) ALS_TRACE(stile, 0);
+        if (r >= 0 && lt == 0) ALS_TRACE(stile - 1, 0);
         // (a) transpose: 16-byte chunk q of the raw row -> plane (q & 3), pixel (q >> 2).  Both sides conflict free.
-        asm volatile("bar.sync 1, %0;" ::"n"(kLoaderThreads) : "memory");  // the previous row has been read out of `can`
-        const unsigned char* raw = raw_base + s * kRawSlotBytes;
-        const int lo_px = mt.first ? 1 : 0;
+        asm volatile("bar.sync %0, %1;" ::"r"(1 + grp), "n"(kLoaderThreads) : "memory");  // previous row read out of `can_g`
+        // chunk q = lt + 128 * it: plane lt & 3 (128 is a multiple of 4), pixel (lt >> 2) + 32 * it; 516 chunks in all
+        const unsigned char* src = raw_base + s * kRawSlotBytes + lt * 16;
+        unsigned char* dst = can_g + (lt & 3) * kPlaneBytes + (lt >> 2) * 16;
+        const int px0 = lt >> 2;
+        const int lo_px = mt.zero ? (1 << 30) : (mt.first ? 1 : 0);  // pixels below lo_px / above valid are padding
+        float4 t[5];
 #pragma unroll
-        for (int q = lt; q < kSlotPx * 4; q += kLoaderThreads) {
-          const int px = q >> 2, ch = q & 3;
-          float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-          if (!mt.zero && px >= lo_px && px <= mt.valid) v = *reinterpret_cast<const float4*>(raw + q * 16);
-          *reinterpret_cast<float4*>(can + ch * kPlaneBytes + px * 16) = v;
+        for (int it = 0; it < 5; ++it) {
+          t[it] = make_float4(0.f, 0.f, 0.f, 0.f);
+          const int px = px0 + 32 * it;
+          if ((it < 4 || lt < 4) && px >= lo_px && px <= mt.valid) t[it] = *reinterpret_cast<const float4*>(src + it * 2048);
         }
-        asm volatile("bar.sync 1, %0;" ::"n"(kLoaderThreads) : "memory");
+#pragma unroll
+        for (int it = 0; it < 5; ++it)
+          if (it < 4 || lt < 4) *reinterpret_cast<float4*>(dst + it * 512) = t[it];
+        asm volatile("bar.sync %0, %1;" ::"r"(1 + grp), "n"(kLoaderThreads) : "memory");
         if (lane == 0) mbar_arrive(&empty_raw[s]);
         // (b) this thread's pixel (slot pixel m + 1) and its left neighbour (slot pixel m) -> tensor memory
-        mbar_wait(&empty_a[rb], pha ^ 1u);  // the MMAs that read this ring slot have completed
+        mbar_wait(&empty_a[rb], static_cast<uint32_t>(((rs / kARing) & 1) ^ 1));  // the MMAs that read this slot completed
         tc05::fence_after_sync();
         const uint32_t t_row = t_lane + rb * kARowCols;
         float4 v[4];
 #pragma unroll
-        for (int c = 0; c < 4; ++c) v[c] = *reinterpret_cast<const float4*>(can + c * kPlaneBytes + (m + 1) * 16);
+        for (int c = 0; c < 4; ++c) v[c] = *reinterpret_cast<const float4*>(can_g + c * kPlaneBytes + (m + 1) * 16);
         store_split(t_row, v);
 #pragma unroll
-        for (int c = 0; c < 4; ++c) v[c] = *reinterpret_cast<const float4*>(can + c * kPlaneBytes + m * 16);
+        for (int c = 0; c < 4; ++c) v[c] = *reinterpret_cast<const float4*>(can_g + c * kPlaneBytes + m * 16);
         store_split(t_row + 32, v);
         tc05::st_wait();
         tc05::fence_before_sync();
         __syncwarp();
         if (lane == 0) mbar_arrive(&full_a[rb]);
-        if (r >= 0) {
-          if (lt == 0) ALS_TRACE(stile, 1);
-          ++stile;
-        }
-        if (++s == kRawStages) { s = 0; phs ^= 1u; }
-        if (++rb == kARing) { rb = 0; pha ^= 1u; }
+        if (r >= 0 && lt == 0) ALS_TRACE(stile - 1, 1);
       }
     }
   } else {
@@ -382,7 +403,7 @@ __global__ void __launch_bounds__(kHeadThreads, 1) score_head_kernel(const HeadP
       const bool valid = m < un.valid;
       for (int k = 0; k < un.rows; ++k, ++tile) {
         if ((tile % kAccStages) != a) continue;
-        mbar_wait(&full_acc[a], static_cast<uint32_t>((tile / kAccStages) & 1));
+        mbar_wait_relaxed(&full_acc[a], static_cast<uint32_t>((tile / kAccStages) & 1));
         tc05::fence_after_sync();
         if (quarter == 0 && lane == 0) ALS_TRACE(tile, 4);
         float conf[4];
@@ -431,7 +452,7 @@ __global__ void __launch_bounds__(kHeadThreads, 1) score_head_kernel(const HeadP
 
   tc05::fence_before_sync();
   __syncthreads();
-  if (warp == 1) tc05::tmem_dealloc<kTmemCols>(tmem);
+  if (warp == kMmaWarp) tc05::tmem_dealloc<kTmemCols>(tmem);
 }
 
 // ---- host side -------------------------------------------------------------------------------------
@@ -518,7 +539,7 @@ HeadPlan plan_head(int C, int measure, int num_sms) {
   const HeadGeom g = head_geometry(C);
   plan.block = kHeadThreads;
   plan.grid = num_sms;
-  plan.smem_bytes = kHeaderBytes + kRawStages * kRawSlotBytes + kCanBytes + 2 * 4 * g.rows * 16;
+  plan.smem_bytes = kHeaderBytes + kRawStages * kRawSlotBytes + kLoaderGroups * kCanBytes + 2 * 4 * g.rows * 16;
   auto agrees = [&](int cb, int n0, int n1, int n2, int n3, int rows) {
     return g.CB == cb && g.n[0] == n0 && g.n[1] == n1 && g.n[2] == n2 && g.n[3] == n3 && g.rows == rows && g.col0[0] == 0 &&
            g.col0[1] == 0 && g.col0[2] == cb && g.col0[3] == cb && g.row0[1] == n0 && g.row0[2] == n0 + n1 &&
