@@ -282,18 +282,20 @@ __global__ void __launch_bounds__(kHeadThreads, 1) score_head_kernel(const HeadP
     constexpr uint32_t kWPart = 4 * kLboB;           // one precision part of the weights
     const uint64_t b_base = tc05::smem_desc(smem_u32(w_base), kLboB, 128);
     mbar_wait(wbar, 0);
-    long long seq = 0;  // feature rows consumed so far (position in the A-row ring)
-    long long tile = 0;
+    static_assert((kARing & (kARing - 1)) == 0, "ring positions are masked");
+    uint32_t seq = 0;   // feature rows consumed so far: ring slot = seq & (kARing - 1), phase = (seq / kARing) & 1
+    uint32_t tile = 0;  // (trace only)
+    int a = 0;          // accumulator stage of the next tile and its phase
+    uint32_t acc_ph = 0;
     for (long long u = blockIdx.x; u < p.n_units; u += gridDim.x) {
       const Unit un = decode_unit(p, u);
       // halo row of the unit
-      mbar_wait(&full_a[seq % kARing], static_cast<uint32_t>((seq / kARing) & 1));
+      mbar_wait(&full_a[seq & (kARing - 1)], (seq / kARing) & 1u);
       for (int k = 0; k < un.rows; ++k) {
-        const long long sp = seq + k, sc = seq + k + 1;
-        const int rb_prev = static_cast<int>(sp % kARing), rb_cur = static_cast<int>(sc % kARing);
-        mbar_wait(&full_a[rb_cur], static_cast<uint32_t>((sc / kARing) & 1));
-        const int a = static_cast<int>(tile % kAccStages);
-        mbar_wait(&empty_acc[a], static_cast<uint32_t>(((tile / kAccStages) & 1) ^ 1));
+        const uint32_t sp = seq + k, sc = seq + k + 1;
+        const int rb_prev = sp & (kARing - 1), rb_cur = sc & (kARing - 1);
+        mbar_wait(&full_a[rb_cur], (sc / kARing) & 1u);
+        mbar_wait(&empty_acc[a], acc_ph ^ 1u);
         tc05::fence_after_sync();
         if (leader) {
           ALS_TRACE(tile, 2);
@@ -324,6 +326,7 @@ __global__ void __launch_bounds__(kHeadThreads, 1) score_head_kernel(const HeadP
         }
         __syncwarp();
         ++tile;
+        if (++a == kAccStages) { a = 0; acc_ph ^= 1u; }
       }
       seq += un.rows + 1;
     }
@@ -335,21 +338,26 @@ __global__ void __launch_bounds__(kHeadThreads, 1) score_head_kernel(const HeadP
     const int m = quarter * 32 + lane;                   // A row = accumulator row = quad column inside the strip
     const uint32_t t_lane = tmem + (static_cast<uint32_t>(quarter * 32) << 16) + kACol0;
     unsigned char* can_g = can + grp * kCanBytes;
-    long long rs = 0;     // feature rows seen so far (ring positions are derived from it)
-    long long stile = 0;
+    uint32_t rs = 0;      // feature rows seen so far: A-ring slot = rs & (kARing - 1)
+    int s = 0;            // raw-ring slot of row rs and its phase
+    uint32_t phs = 0;
+    uint32_t stile = 0;   // (trace only)
     for (long long u = blockIdx.x; u < p.n_units; u += gridDim.x) {
       const Unit un = decode_unit(p, u);
       for (int r = -1; r < un.rows; ++r, ++rs) {
         if (r >= 0) ++stile;
-        if ((rs & 1) != grp) continue;
-        const int s = static_cast<int>(rs % kRawStages), rb = static_cast<int>(rs % kARing);
-        mbar_wait(&full_raw[s], static_cast<uint32_t>((rs / kRawStages) & 1));
-        const RawMeta mt = meta[s];
+        const int s_row = s;
+        const uint32_t phs_row = phs;
+        if (++s == kRawStages) { s = 0; phs ^= 1u; }
+        if ((rs & 1u) != static_cast<uint32_t>(grp)) continue;
+        const int rb = rs & (kARing - 1);
+        mbar_wait(&full_raw[s_row], phs_row);
+        const RawMeta mt = meta[s_row];
         if (r >= 0 && lt == 0) ALS_TRACE(stile - 1, 0);
         // (a) transpose: 16-byte chunk q of the raw row -> plane (q & 3), pixel (q >> 2).  Both sides conflict free.
         asm volatile("bar.sync %0, %1;" ::"r"(1 + grp), "n"(kLoaderThreads) : "memory");  // previous row read out of `can_g`
         // chunk q = lt + 128 * it: plane lt & 3 (128 is a multiple of 4), pixel (lt >> 2) + 32 * it; 516 chunks in all
-        const unsigned char* src = raw_base + s * kRawSlotBytes + lt * 16;
+        const unsigned char* src = raw_base + s_row * kRawSlotBytes + lt * 16;
         unsigned char* dst = can_g + (lt & 3) * kPlaneBytes + (lt >> 2) * 16;
         const int px0 = lt >> 2;
         const int lo_px = mt.zero ? (1 << 30) : (mt.first ? 1 : 0);  // pixels below lo_px / above valid are padding
@@ -364,9 +372,9 @@ __global__ void __launch_bounds__(kHeadThreads, 1) score_head_kernel(const HeadP
         for (int it = 0; it < 5; ++it)
           if (it < 4 || lt < 4) *reinterpret_cast<float4*>(dst + it * 512) = t[it];
         asm volatile("bar.sync %0, %1;" ::"r"(1 + grp), "n"(kLoaderThreads) : "memory");
-        if (lane == 0) mbar_arrive(&empty_raw[s]);
+        if (lane == 0) mbar_arrive(&empty_raw[s_row]);
         // (b) this thread's pixel (slot pixel m + 1) and its left neighbour (slot pixel m) -> tensor memory
-        mbar_wait(&empty_a[rb], static_cast<uint32_t>(((rs / kARing) & 1) ^ 1));  // the MMAs that read this slot completed
+        mbar_wait(&empty_a[rb], ((rs / kARing) & 1u) ^ 1u);  // the MMAs that read this slot completed
         tc05::fence_after_sync();
         const uint32_t t_row = t_lane + rb * kARowCols;
         float4 v[4];
@@ -393,7 +401,9 @@ __global__ void __launch_bounds__(kHeadThreads, 1) score_head_kernel(const HeadP
     const ScoreParams& sp = p.sp;
     const int W = 2 * p.w;
     ImageAcc acc;
-    long long tile = 0;
+    uint32_t tile = 0;   // tiles of this CTA so far; this warp serves tiles a, a + kAccStages, ...
+    uint32_t mine = a;
+    uint32_t ph = 0;
     for (long long u = blockIdx.x; u < p.n_units; u += gridDim.x) {
       const Unit un = decode_unit(p, u);
       if (un.n != acc.img) {
@@ -402,8 +412,10 @@ __global__ void __launch_bounds__(kHeadThreads, 1) score_head_kernel(const HeadP
       }
       const bool valid = m < un.valid;
       for (int k = 0; k < un.rows; ++k, ++tile) {
-        if ((tile % kAccStages) != a) continue;
-        mbar_wait_relaxed(&full_acc[a], static_cast<uint32_t>((tile / kAccStages) & 1));
+        if (tile != mine) continue;
+        mine += kAccStages;
+        mbar_wait_relaxed(&full_acc[a], ph);
+        ph ^= 1u;
         tc05::fence_after_sync();
         if (quarter == 0 && lane == 0) ALS_TRACE(tile, 4);
         float conf[4];
