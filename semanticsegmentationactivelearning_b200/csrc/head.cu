@@ -74,7 +74,7 @@ constexpr int kPlaneBytes = (kSlotPx + 1) * 16;       // 2080: stride between th
 constexpr int kCanBytes = 4 * kPlaneBytes;            // 8320: one transposed row
 // Warp roles by warp id.  The SM's issue arbiter favours HIGHER warp ids, so the roles on the critical path
 // (producer, MMA issuer, loaders) sit above the twelve epilogue warps, which mostly wait.
-constexpr int kLoaderGroups = 2;                      // two groups of four warps take alternate feature rows
+constexpr int kLoaderGroups = 2;                      // groups of four warps taking alternate feature rows
 constexpr int kLoaderThreads = 128;                   // per group
 constexpr int kFirstEpilogueWarp = 0;                 // warps 0..11: stage = warp >> 2, lane quarter = warp & 3
 constexpr int kFirstLoaderWarp = 4 * kAccStages;      // warps 12..19
@@ -349,7 +349,7 @@ __global__ void __launch_bounds__(kHeadThreads, 1) score_head_kernel(const HeadP
         const int s_row = s;
         const uint32_t phs_row = phs;
         if (++s == kRawStages) { s = 0; phs ^= 1u; }
-        if ((rs & 1u) != static_cast<uint32_t>(grp)) continue;
+        if (kLoaderGroups > 1 && (rs & (kLoaderGroups - 1)) != static_cast<uint32_t>(grp)) continue;
         const int rb = rs & (kARing - 1);
         mbar_wait(&full_raw[s_row], phs_row);
         const RawMeta mt = meta[s_row];
