@@ -158,20 +158,34 @@ def cpu_reference_rate(w, seconds: float, dtype: str):
     cores = RT.set_threads()
     T, H, W, C = w["T"], w["H"], w["W"], w["C"]
     n_img = 2
-    x = torch.from_numpy(synth.synth_logits(T, 0, n_img, H, W, C, seed=SEED, squeeze_t=False))
-    if T == 1:
-        x = x[0]
-    RT.score_pool(x[:1] if T == 1 else x[:, :1], w["measure"])          # warm-up
+    if w.get("head"):
+        x, kern = _cpu_head_inputs(w, n_img)
+        run = lambda xx: RT.score_pool(RT.final_head(xx, kern), w["measure"])
+    else:
+        x = torch.from_numpy(synth.synth_logits(T, 0, n_img, H, W, C, seed=SEED, squeeze_t=False))
+        if T == 1:
+            x = x[0]
+        run = lambda xx: RT.score_pool(xx, w["measure"])
+    run(x[:1] if (T == 1 or w.get("head")) else x[:, :1])               # warm-up
     t0 = time.perf_counter()
     done = 0
     while True:
-        RT.score_pool(x, w["measure"])
+        run(x)
         done += n_img
         el = time.perf_counter() - t0
         if el >= seconds or done >= 64:
             break
     rate = done * H * W / el
     return rate, cores, "%d images x T=%d @%dx%dx%d, %s, torch CPU op-by-op, %.1f s" % (done, T, H, W, C, w["measure"], el)
+
+
+def _cpu_head_inputs(w, n_img):
+    """Random-init `Final` input and kernel for the CPU legs of the fused-head workloads."""
+    import torch
+    g = torch.Generator().manual_seed(SEED)
+    x = torch.randn((n_img, w["H"] // 2, w["W"] // 2, 16), generator=g)
+    kern = torch.from_numpy((0.4 * np.random.default_rng(SEED).standard_normal((3, 3, w["C"], 16))).astype(np.float32))
+    return x, kern
 
 
 def run_reference(args):
@@ -186,15 +200,19 @@ def run_reference(args):
     cores = RT.set_threads()
     T, H, W, C = w["T"], w["H"], w["W"], w["C"]
     n_img = 2                                   # images per step (bounded sample of the pool)
-    x = torch.from_numpy(synth.synth_logits(T, 0, n_img, H, W, C, seed=SEED, squeeze_t=False))
-    if T == 1:
-        x = x[0]
+    kern = None
+    if w.get("head"):
+        x, kern = _cpu_head_inputs(w, n_img)
+    else:
+        x = torch.from_numpy(synth.synth_logits(T, 0, n_img, H, W, C, seed=SEED, squeeze_t=False))
+        if T == 1:
+            x = x[0]
     unl = np.arange(n_img)
     for _ in range(max(args.warmup, 1)):
-        RT.rank_confidence(x, unl, 1, w["measure"], batch_size=8)
+        RT.rank_confidence(x, unl, 1, w["measure"], batch_size=8, head_kernel=kern)
     t0 = time.perf_counter()
     for _ in range(args.steps):
-        RT.rank_confidence(x, unl, 1, w["measure"], batch_size=8)
+        RT.rank_confidence(x, unl, 1, w["measure"], batch_size=8, head_kernel=kern)
     el = time.perf_counter() - t0
     rate = args.steps * n_img * H * W / el / 1e9
     sample = "%d images x T=%d @%dx%dx%d per step (bounded sample of the %d-image pool), %s" % (
@@ -444,6 +462,16 @@ def main():
             "cpu_baseline": cpu,
             "selected_ids_head": [int(i) for i in ids[:5]],
         }
+        if head:
+            # the fused kernel is not HBM bound: say what limits it and how busy the tensor pipe is
+            from semanticsegmentationactivelearning_b200.acquisition import head_mma_flops_per_pixel
+            fl = head_mma_flops_per_pixel(C)
+            line["roofline"]["limiter"] = ("SM issue slots + MUFU (19 ex2 + lg2 + rcp per pixel); ncu: XU pipe 66 %, tensor pipe 59 %, "
+                                           "issue 57 %, DRAM 23 % (profiles/r01_ncu_full_cfg1h.txt)")
+            line["roofline"]["tensor"] = {"kind": "tf32, 3-product split (hi*lo + lo*hi + hi*hi)", "flops_per_pixel": fl,
+                                          "achieved_tflops": fl * chunks[0][2] * P / (avg_ms * 1e-3) / 1e12,
+                                          "nominal_peak_tflops": 1100.0}
+            line["config"]["input"] = "Final-layer input [N,%d,%d,16] fp32 + kernel [3,3,%d,16]; logits never materialised" % (H // 2, W // 2, C)
         print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()

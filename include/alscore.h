@@ -138,6 +138,17 @@ ALS_API int als_score_dlpack(als_ctx* ctx, void* managed, int measure, double* s
  */
 ALS_API int als_head_prepare(als_ctx* ctx, const float* kernel, int64_t C);
 
+/*
+ * Host-only helpers (no GPU needed; used by the CPU tests of the operand packing):
+ * als_head_geometry fills geom[14] = {C, CB, n[0..3], col0[0..3], row0[0..3]} followed by the total row count
+ * in *rows: the accumulator has 4 blocks of CB = round_up(C,4) columns, one per pixel of the 2x2 output quad,
+ * in the order (dy,dx) = (0,1) (0,0) (1,0) (1,1); operand o multiplies source pixel (i - (o&1), j - (o>>1)),
+ * is n[o] columns wide, starts at accumulator column col0[o] and at row row0[o] of the packed image.
+ * als_head_pack_weights writes out[2][4][rows][4] floats (tf32 hi part, lo part; 16-byte channel chunks).
+ */
+ALS_API int als_head_geometry(int64_t C, int32_t* geom14, int32_t* rows);
+ALS_API int als_head_pack_weights(const float* kernel, int64_t C, float* out, int64_t out_floats);
+
 /* 1 if a fused-head kernel exists for (C, measure), else 0. */
 ALS_API int als_head_supported(int64_t C, int measure);
 

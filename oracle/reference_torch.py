@@ -60,6 +60,16 @@ def _measure(prob: torch.Tensor, measure: str, C: int) -> torch.Tensor:
     raise NotImplementedError("Uncertainty function not implemented.")  # :259-260
 
 
+def final_head(features: torch.Tensor, kernel: torch.Tensor) -> torch.Tensor:
+    """`Final.call` (models/enet/enet_modules.py:1359-1381): tf.nn.conv2d_transpose(features [N,h,w,16],
+    kernel [3,3,C,16], output [N,2h,2w,C], strides 2, padding SAME).  torch's conv_transpose2d without padding
+    yields the full (2h+1) x (2w+1) result; TF's SAME padding drops the last row and column."""
+    n, h, w, _ = features.shape
+    wt = kernel.permute(3, 2, 0, 1).contiguous()                 # [in, out, kh, kw]
+    full = torch.nn.functional.conv_transpose2d(features.permute(0, 3, 1, 2), wt, stride=2)
+    return full[:, :, :2 * h, :2 * w].permute(0, 2, 3, 1).contiguous()
+
+
 def score_pool(logits: torch.Tensor, measure: str) -> torch.Tensor:
     """Per-image f64 mean of the f32 map (:261-263)."""
     conf = pixel_confidence(logits, measure)
@@ -67,12 +77,15 @@ def score_pool(logits: torch.Tensor, measure: str) -> torch.Tensor:
 
 
 def rank_confidence(logits: torch.Tensor, unlabelled: np.ndarray, selection_size: int, measure: str,
-                    batch_size: int = 8):
-    """:682-715 with the TF graph replaced by the torch restatement; selection is verbatim NumPy."""
+                    batch_size: int = 8, head_kernel: torch.Tensor | None = None):
+    """:682-715 with the TF graph replaced by the torch restatement; selection is verbatim NumPy.
+    With ``head_kernel`` the first argument is the `Final` layer's input and the layer runs first (enet.py:367)."""
     n = logits.shape[-4]
     confidence = np.zeros(n, dtype=np.float32)
     for i in range(0, n, batch_size):
         xb = logits[i:i + batch_size] if logits.dim() == 4 else logits[:, i:i + batch_size]
+        if head_kernel is not None:
+            xb = final_head(xb, head_kernel)
         confidence[i:i + batch_size] = score_pool(xb, measure).numpy()
     unlabelled_confidence = confidence[unlabelled]
     selection_size = np.minimum(len(unlabelled), selection_size)

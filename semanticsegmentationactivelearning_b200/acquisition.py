@@ -368,6 +368,17 @@ class Scorer:
                 "stages": st.value, "tile_pixels": tp.value}
 
 
+def head_mma_flops_per_pixel(num_classes: int) -> float:
+    """Tensor-core FLOPs the fused head issues per OUTPUT pixel (zero padding of the narrow operands included):
+    per tile of 128 input pixels, 3 products x 2 k-steps x (N0 + N1 + N2 + N3) x 128 x 8 MACs (csrc/head.cu)."""
+    cb = (int(num_classes) + 3) // 4 * 4
+    r16 = lambda v: (v + 15) // 16 * 16
+    n1 = n2 = r16(2 * cb)
+    n3 = r16(cb)
+    n0 = max(r16(4 * cb), n1, cb + n2, cb + n3)
+    return 2.0 * 128 * 8 * 6 * (n0 + n1 + n2 + n3) / 512.0
+
+
 _USED_NAME = b"used_dltensor"   # module-level: PyCapsule_SetName keeps the pointer, not a copy
 
 _default_scorers = {}

@@ -598,6 +598,30 @@ int als_head_supported(int64_t C, int measure) {
   return als::plan_head(static_cast<int>(C), measure, 1).func != nullptr ? 1 : 0;
 }
 
+int als_head_geometry(int64_t C, int32_t* geom14, int32_t* rows) {
+  if (!geom14 || !rows) return fail(nullptr, ALS_ERR_INVALID, "NULL argument");
+  if (C < 2 || C > 32) return fail(nullptr, ALS_ERR_INVALID, "the fused head handles 2 <= C <= 32 classes, got %lld", (long long)C);
+  const als::HeadGeom g = als::head_geometry(static_cast<int>(C));
+  geom14[0] = g.C;
+  geom14[1] = g.CB;
+  for (int o = 0; o < 4; ++o) {
+    geom14[2 + o] = g.n[o];
+    geom14[6 + o] = g.col0[o];
+    geom14[10 + o] = g.row0[o];
+  }
+  *rows = g.rows;
+  return ALS_OK;
+}
+
+int als_head_pack_weights(const float* kernel, int64_t C, float* out, int64_t out_floats) {
+  if (!kernel || !out) return fail(nullptr, ALS_ERR_INVALID, "NULL argument");
+  if (C < 2 || C > 32) return fail(nullptr, ALS_ERR_INVALID, "the fused head handles 2 <= C <= 32 classes, got %lld", (long long)C);
+  const als::HeadGeom g = als::head_geometry(static_cast<int>(C));
+  if (out_floats < static_cast<int64_t>(2) * 4 * g.rows * 4) return fail(nullptr, ALS_ERR_INVALID, "output buffer too small");
+  als::pack_head_weights(kernel, static_cast<int>(C), out);
+  return ALS_OK;
+}
+
 int als_head_prepare(als_ctx* ctx, const float* kernel, int64_t C) {
   if (!ctx) return fail(nullptr, ALS_ERR_INVALID, "context is NULL");
   if (!kernel) return fail(ctx, ALS_ERR_INVALID, "kernel pointer is NULL");
