@@ -66,21 +66,13 @@ namespace {
 constexpr int kRawStages = 6;
 constexpr int kARing = 4;                             // feature rows resident in tensor memory (2 in use by the MMAs, 2 being written)
 constexpr int kARowCols = 64;                         // [own hi 16 | own lo 16 | left hi 16 | left lo 16]
-constexpr int kAccStages = 3;
 constexpr int kTmemCols = 512;
 constexpr int kSlotPx = kHeadTileQuads + 1;           // 129 pixels: one halo pixel on the left
 constexpr int kRawSlotBytes = 8320;                   // 129 * 64 rounded up to 128
 constexpr int kPlaneBytes = (kSlotPx + 1) * 16;       // 2080: stride between the 16-byte chunk planes of the transposed row
 constexpr int kCanBytes = 4 * kPlaneBytes;            // 8320: one transposed row
-// Warp roles by warp id.  The SM's issue arbiter favours HIGHER warp ids, so the roles on the critical path
-// (producer, MMA issuer, loaders) sit above the twelve epilogue warps, which mostly wait.
 constexpr int kLoaderGroups = 2;                      // groups of four warps taking alternate feature rows
 constexpr int kLoaderThreads = 128;                   // per group
-constexpr int kFirstEpilogueWarp = 0;                 // warps 0..11: stage = warp >> 2, lane quarter = warp & 3
-constexpr int kFirstLoaderWarp = 4 * kAccStages;      // warps 12..19
-constexpr int kMmaWarp = kFirstLoaderWarp + 4 * kLoaderGroups;  // 20
-constexpr int kProducerWarp = kMmaWarp + 1;           // 21
-constexpr int kHeadThreads = 32 * (kProducerWarp + 1);  // 704
 constexpr int kHeaderBytes = 512;
 
 struct RawMeta {
@@ -116,8 +108,18 @@ template <int C>
 struct Geom {
   static constexpr int CB = cround(C, 4);
   static constexpr int N1 = cround(2 * CB, 16), N2 = cround(2 * CB, 16), N3 = cround(CB, 16);
-  static constexpr int N0 = cmax(cround(4 * CB, 16), cmax(N1, cmax(CB + N2, CB + N3)));
+  static constexpr int N0 = cround(cmax(4 * CB, cmax(N1, cmax(CB + N2, CB + N3))), 16);  // also initialises every column
   static constexpr int ROWS = N0 + N1 + N2 + N3;
+  // accumulator stages that fit beside the A-row ring in the 512 tensor-memory columns (3 up to C = 20, else 2)
+  static constexpr int ACC_STAGES = (cround(3 * N0, 32) + kARing * kARowCols <= kTmemCols) ? 3 : 2;
+  static constexpr int A_COL0 = cround(ACC_STAGES * N0, 32);  // first column of the A-row ring
+  static_assert(A_COL0 + kARing * kARowCols <= kTmemCols, "tensor memory budget");
+  // Warp roles by warp id.  The SM's issue arbiter favours HIGHER warp ids, so the roles on the critical path
+  // (producer, MMA issuer, loaders) sit above the epilogue warps, which mostly wait.
+  static constexpr int FIRST_LOADER_WARP = 4 * ACC_STAGES;  // warps below: epilogue, stage = warp >> 2, lane quarter = warp & 3
+  static constexpr int MMA_WARP = FIRST_LOADER_WARP + 4 * kLoaderGroups;
+  static constexpr int PRODUCER_WARP = MMA_WARP + 1;
+  static constexpr int THREADS = 32 * (PRODUCER_WARP + 1);   // 704 (3 stages) or 576 (2 stages)
 };
 
 // TMEM -> registers, CNT consecutive columns (CNT multiple of 4, <= 32)
@@ -190,12 +192,14 @@ __device__ __forceinline__ void store_split(uint32_t taddr, const float4 (&v)[4]
 }
 
 template <int C, int MEASURE>
-__global__ void __launch_bounds__(kHeadThreads, 1) score_head_kernel(const HeadParams p) {
+__global__ void __launch_bounds__(Geom<C>::THREADS, 1) score_head_kernel(const HeadParams p) {
   using G = Geom<C>;
   constexpr int CB = G::CB;
-  constexpr int kAccStride = G::N0;                                  // accumulator columns per stage
-  constexpr int kACol0 = (kAccStages * kAccStride + 31) / 32 * 32;  // first column of the A-row ring
-  static_assert(kACol0 + kARing * kARowCols <= kTmemCols, "tensor memory budget");
+  constexpr int kAccStages = G::ACC_STAGES;
+  constexpr int kAccStride = G::N0;   // accumulator columns per stage
+  constexpr int kACol0 = G::A_COL0;   // first column of the A-row ring
+  constexpr int kFirstLoaderWarp = G::FIRST_LOADER_WARP, kMmaWarp = G::MMA_WARP, kProducerWarp = G::PRODUCER_WARP;
+  constexpr int kFirstEpilogueWarp = 0;
   constexpr int wpart_bytes = 4 * G::ROWS * 16;  // one precision part of the packed weights
 
   extern __shared__ __align__(128) unsigned char smem[];
@@ -540,26 +544,40 @@ static const void* pick_head(int measure, const char** name) {
   }
 }
 
+// One instantiation per class count 2..32 (the reference's datasets use 19, 6 and 19: datasets/*.py num_classes).
+#define ALS_HEAD_C_LIST(X) X(2) X(3) X(4) X(5) X(6) X(7) X(8) X(9) X(10) X(11) X(12) X(13) X(14) X(15) X(16) X(17) X(18) \
+  X(19) X(20) X(21) X(22) X(23) X(24) X(25) X(26) X(27) X(28) X(29) X(30) X(31) X(32)
+
+template <int C>
+static bool geometry_agrees(const HeadGeom& g) {
+  using T = Geom<C>;
+  return g.CB == T::CB && g.n[0] == T::N0 && g.n[1] == T::N1 && g.n[2] == T::N2 && g.n[3] == T::N3 && g.rows == T::ROWS &&
+         g.col0[0] == 0 && g.col0[1] == 0 && g.col0[2] == T::CB && g.col0[3] == T::CB && g.row0[1] == T::N0 &&
+         g.row0[2] == T::N0 + T::N1 && g.row0[3] == T::N0 + T::N1 + T::N2;
+}
+
 HeadPlan plan_head(int C, int measure, int num_sms) {
   HeadPlan plan{};
+  const HeadGeom g = head_geometry(C);
+  bool same = false;
   switch (C) {
-    case 6: plan.func = pick_head<6>(measure, &plan.name); break;
-    case 19: plan.func = pick_head<19>(measure, &plan.name); break;
+#define X(c)                                       \
+  case c:                                          \
+    plan.func = pick_head<c>(measure, &plan.name); \
+    plan.block = Geom<c>::THREADS;                 \
+    same = geometry_agrees<c>(g);                  \
+    break;
+    ALS_HEAD_C_LIST(X)
+#undef X
     default: plan.func = nullptr; break;
   }
   if (!plan.func) return plan;
-  const HeadGeom g = head_geometry(C);
-  plan.block = kHeadThreads;
+  if (!same) {  // host packing and device geometry disagree: refuse rather than mis-compute
+    plan.func = nullptr;
+    return plan;
+  }
   plan.grid = num_sms;
   plan.smem_bytes = kHeaderBytes + kRawStages * kRawSlotBytes + kLoaderGroups * kCanBytes + 2 * 4 * g.rows * 16;
-  auto agrees = [&](int cb, int n0, int n1, int n2, int n3, int rows) {
-    return g.CB == cb && g.n[0] == n0 && g.n[1] == n1 && g.n[2] == n2 && g.n[3] == n3 && g.rows == rows && g.col0[0] == 0 &&
-           g.col0[1] == 0 && g.col0[2] == cb && g.col0[3] == cb && g.row0[1] == n0 && g.row0[2] == n0 + n1 &&
-           g.row0[3] == n0 + n1 + n2;
-  };
-  const bool same = (C == 6) ? agrees(Geom<6>::CB, Geom<6>::N0, Geom<6>::N1, Geom<6>::N2, Geom<6>::N3, Geom<6>::ROWS)
-                             : agrees(Geom<19>::CB, Geom<19>::N0, Geom<19>::N1, Geom<19>::N2, Geom<19>::N3, Geom<19>::ROWS);
-  if (!same) plan.func = nullptr;  // host packing and device geometry disagree: refuse rather than mis-compute
   return plan;
 }
 

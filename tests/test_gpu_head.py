@@ -71,9 +71,9 @@ def _check_maps(got, feat, kern, measure, threshold=0.6, logits32=None):
     return float(err_gpu.max()), float(err_ref.max())
 
 
-@pytest.mark.parametrize("C", [19, 6])
-@pytest.mark.parametrize("shape", [(3, 37, 150), (2, 8, 128), (1, 1, 1), (2, 5, 129), (1, 70, 300)],
-                         ids=lambda s: "N%d_%dx%d" % s)
+@pytest.mark.parametrize("C,shape", [(c, s) for c in (19, 6) for s in [(3, 37, 150), (2, 8, 128), (1, 1, 1), (2, 5, 129), (1, 70, 300)]]
+                         + [(c, (2, 9, 140)) for c in (2, 3, 4, 5, 8, 12, 13, 16, 20, 21, 24, 27, 32)],
+                         ids=lambda v: str(v) if isinstance(v, int) else "N%d_%dx%d" % v)
 def test_fused_head_vs_oracle(torch, scorer, C, shape):
     from oracle import reference_np as R
     N, h, w = shape
@@ -128,7 +128,9 @@ def test_fused_head_validation(torch, scorer):
     with pytest.raises(ValueError):
         scorer.prepare_head(np.zeros((3, 3, 19, 8), np.float32))
     with pytest.raises(NotImplementedError):
-        scorer.prepare_head(np.zeros((3, 3, 23, 16), np.float32))       # no fused kernel for C=23
+        scorer.prepare_head(np.zeros((3, 3, 33, 16), np.float32))       # fused kernels exist for 2 <= C <= 32
+    assert all(scorer.head_supported(c, m) for c in range(2, 33) for m in MEASURES)
+    assert not scorer.head_supported(33) and not scorer.head_supported(19, "variance")
     scorer.prepare_head(np.zeros((3, 3, 19, 16), np.float32))
     f = torch.zeros((1, 4, 4, 16), device="cuda")
     with pytest.raises(NotImplementedError):
