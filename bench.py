@@ -325,7 +325,8 @@ def main():
             ids, conf = sc.pool_select(unl_local, K_SELECT)
         else:
             scores = sc.pool_scores(N)
-            ids, conf = rank_confidence_sharded(scores, id0 + unl_local, unl_global, K_SELECT, scorer=sc)
+            ids, conf = rank_confidence_sharded(scores, id0 + unl_local, unl_global, K_SELECT, scorer=sc,
+                                                    max_unlabelled_per_rank=N)
         return ids, conf
 
     def barrier():

@@ -39,7 +39,8 @@ def merge_candidates(keys: np.ndarray, ids: np.ndarray, k: int, select: Callable
 
 
 def rank_confidence_sharded(local_scores: np.ndarray, local_ids: np.ndarray, unlabelled, selection_size: int, *,
-                            group=None, select: Optional[Callable] = None, scorer=None):
+                            group=None, select: Optional[Callable] = None, scorer=None,
+                            max_unlabelled_per_rank: Optional[int] = None):
     """Global selection from per-rank results.
 
     local_scores   f32[n_local]  this rank's per-image confidences (rounded to f32 as :700 does)
@@ -47,6 +48,12 @@ def rank_confidence_sharded(local_scores: np.ndarray, local_ids: np.ndarray, unl
     unlabelled     the global unlabelled index array (same on every rank)
     Returns the reference tuple (low_conf_examples, unlabelled_confidence) (:715), identical on all ranks.
     `select(keys, ids, k) -> (keys, ids)` defaults to the CUDA block-radix select of `scorer`.
+
+    Exchange: every rank contributes one byte record [count | k candidate keys | k candidate ids | scores | ids].
+    With ``max_unlabelled_per_rank`` (an upper bound on any rank's number of unlabelled images, e.g. the largest shard
+    size; the SAME value on every rank)
+    that is ONE all-gather; without it the record is sent in two parts (counts + candidates first, then the scores
+    padded to the largest count).  The payload is a few hundred KB at most: latency, not bandwidth.
     """
     import torch
     import torch.distributed as dist
@@ -67,35 +74,48 @@ def rank_confidence_sharded(local_scores: np.ndarray, local_ids: np.ndarray, unl
     k = int(max(0, min(int(selection_size), unlabelled.size)))
 
     # candidates: this rank's k lowest among its unlabelled images
-    order = np.argsort(local_ids, kind="stable")
-    pos = np.searchsorted(local_ids[order], unlabelled)
-    pos = np.clip(pos, 0, max(local_ids.size - 1, 0))
-    mine = (local_ids.size > 0) & (local_ids[order][pos] == unlabelled) if local_ids.size else np.zeros(unlabelled.size, bool)
-    my_unl = unlabelled[mine]
-    my_conf = local_scores[order][pos[mine]] if local_ids.size else np.zeros(0, np.float32)
+    if local_ids.size:
+        order = np.argsort(local_ids, kind="stable")
+        sorted_ids = local_ids[order]
+        pos = np.clip(np.searchsorted(sorted_ids, unlabelled), 0, local_ids.size - 1)
+        mine = sorted_ids[pos] == unlabelled
+        my_unl = unlabelled[mine]
+        my_conf = local_scores[order][pos[mine]]
+    else:
+        my_unl = np.zeros(0, np.int64)
+        my_conf = np.zeros(0, np.float32)
     ck, ci = select(my_conf, my_unl, k) if (k > 0 and my_unl.size) else (np.zeros(0, np.float32), np.zeros(0, np.int64))
     pad = k - ck.size
     cand_k = np.concatenate([ck, np.full(pad, np.nan, np.float32)]).astype(np.float32)
     cand_i = np.concatenate([ci, _PAD_ID + rank * max(k, 1) + np.arange(pad, dtype=np.int64)]).astype(np.int64)
 
-    # exchange 1: fixed-size candidate buffers (k * 12 bytes per rank)
-    gk = torch.empty(world * k, dtype=torch.float32, device=dev)
-    gi = torch.empty(world * k, dtype=torch.int64, device=dev)
-    if k > 0:
-        dist.all_gather_into_tensor(gk, torch.from_numpy(cand_k).to(dev), group=group)
-        dist.all_gather_into_tensor(gi, torch.from_numpy(cand_i).to(dev), group=group)
-    # exchange 2: every rank's (id, score) pairs for the histogram consumer (:781-784), padded to the max shard
-    sizes = torch.empty(world, dtype=torch.int64, device=dev)
-    dist.all_gather_into_tensor(sizes, torch.tensor([my_unl.size], dtype=torch.int64, device=dev), group=group)
-    mmax = int(sizes.max().item())
-    sid = np.full(mmax, -1, np.int64); sid[:my_unl.size] = my_unl
-    ssc = np.zeros(mmax, np.float32); ssc[:my_unl.size] = my_conf
-    all_id = torch.empty(world * mmax, dtype=torch.int64, device=dev)
-    all_sc = torch.empty(world * mmax, dtype=torch.float32, device=dev)
-    if mmax > 0:
-        dist.all_gather_into_tensor(all_id, torch.from_numpy(sid).to(dev), group=group)
-        dist.all_gather_into_tensor(all_sc, torch.from_numpy(ssc).to(dev), group=group)
-    all_id = all_id.cpu().numpy(); all_sc = all_sc.cpu().numpy()
+    def gather(record: np.ndarray) -> np.ndarray:
+        """all-gather equal-sized byte records -> [world, len(record)] uint8"""
+        out = torch.empty(world * record.size, dtype=torch.uint8, device=dev)
+        dist.all_gather_into_tensor(out, torch.from_numpy(record).to(dev), group=group)
+        return out.cpu().numpy().reshape(world, record.size)
+
+    def score_part(width: int) -> np.ndarray:
+        sc = np.zeros(width, np.float32); sc[:my_unl.size] = my_conf
+        sid = np.full(width, -1, np.int64); sid[:my_unl.size] = my_unl
+        return np.concatenate([sc.view(np.uint8), sid.view(np.uint8)])
+
+    head = np.concatenate([np.asarray([my_unl.size], np.int64).view(np.uint8), cand_k.view(np.uint8), cand_i.view(np.uint8)])
+    if max_unlabelled_per_rank is not None:
+        width = int(max_unlabelled_per_rank)
+        if my_unl.size > width:
+            raise ValueError("max_unlabelled_per_rank=%d but this rank holds %d unlabelled images" % (width, my_unl.size))
+        both = gather(np.concatenate([head, score_part(width)]))
+        heads, parts = both[:, :head.size], both[:, head.size:]
+    else:
+        heads = gather(head)
+        width = int(heads[:, :8].copy().view(np.int64).max())
+        parts = gather(score_part(width)) if width > 0 else np.zeros((world, 0), np.uint8)
+    gk = heads[:, 8:8 + 4 * k].copy().view(np.float32).reshape(-1)
+    gi = heads[:, 8 + 4 * k:].copy().view(np.int64).reshape(-1)
+    all_sc = parts[:, :4 * width].copy().view(np.float32).reshape(-1)
+    all_id = parts[:, 4 * width:].copy().view(np.int64).reshape(-1)
+
     valid = all_id >= 0
     vid, vsc = all_id[valid], all_sc[valid]
     # unlabelled_confidence = confidence[unlabelled] (:705); unvisited examples keep 0.0 (:685)
@@ -109,5 +129,5 @@ def rank_confidence_sharded(local_scores: np.ndarray, local_ids: np.ndarray, unl
 
     if k == 0:
         return np.zeros(0, np.int64), unlabelled_confidence
-    _, ids = merge_candidates(gk.cpu().numpy(), gi.cpu().numpy(), k, select)
+    _, ids = merge_candidates(gk, gi, k, select)
     return ids, unlabelled_confidence

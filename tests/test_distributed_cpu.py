@@ -41,6 +41,10 @@ def _worker(rank, world, port, cases, out_dir):
             lo, hi = shard_bounds(len(scores), rank, world)
             ids, uconf = rank_confidence_sharded(scores[lo:hi], np.arange(lo, hi), unlabelled, k,
                                                  select=_oracle_select)
+            # the single-collective form (upper bound on a rank's unlabelled count known up front) must agree
+            ids1, uconf1 = rank_confidence_sharded(scores[lo:hi], np.arange(lo, hi), unlabelled, k, select=_oracle_select,
+                                                   max_unlabelled_per_rank=-(-len(scores) // world) + 3)
+            assert np.array_equal(ids, ids1) and np.array_equal(uconf, uconf1, equal_nan=True), name
             np.savez(os.path.join(out_dir, "%s_r%d.npz" % (name, rank)), ids=ids, uconf=uconf)
     finally:
         dist.destroy_process_group()
