@@ -16,4 +16,9 @@ $CMD > /dev/null 2>&1 &&
 ncu --set full --clock-control none --import-source on -k regex:score_tiles -s 4 -c 1 \
     -f -o $OUT/prof_${WL}_${TAG} $CMD > $OUT/ncu_full_${WL}_${TAG}.log 2>&1
 echo "full capture exit $?"
+# summaries are made on the box; the 20 MB report itself only travels back with KEEP_REP=1 (gpurun_out is capped at 64 MiB)
+python profiles/summarize.py full $OUT/prof_${WL}_${TAG}.ncu-rep > $OUT/ncu_full_${WL}_${TAG}.txt 2>&1
+python profiles/stalls.py $OUT/prof_${WL}_${TAG}.ncu-rep 0 20 > $OUT/stalls_${WL}_${TAG}.txt 2>&1
+python profiles/summarize.py launches $OUT/launches_${WL}_${TAG}.csv > $OUT/launches_${WL}_${TAG}.txt 2>&1
+[ "${KEEP_REP:-0}" = "1" ] || rm -f $OUT/prof_${WL}_${TAG}.ncu-rep
 ls -la $OUT | tail -12
