@@ -53,6 +53,8 @@ WORKLOADS = {
     # (16 B per output pixel instead of 4*C) and runs the 16->C transposed convolution on the tensor cores itself
     "cfg1h": dict(N=2975, T=1, H=512, W=1024, C=19, measure="entropy", resident=2975, chunk=425, head=True,
                   desc="fused Final head + entropy, pool 2975 @512x1024 (features 256x512x16), C=19"),
+    "cfg2h": dict(N=2975, T=8, H=512, W=1024, C=19, measure="variance", resident=340, chunk=85, head=True,
+                  desc="fused Final head + MC-dropout T=8 variance, pool 2975 @512x1024 (features 8x256x512x16), C=19"),
     "cfg3h": dict(N=372, T=1, H=1024, W=2048, C=19, measure="margin", resident=372, chunk=124, head=True,
                   desc="fused Final head + margin @1024x2048 (features 512x1024x16), 372 images per GPU"),
     "cfg4h": dict(N=4096, T=1, H=480, W=640, C=6, measure="entropy", resident=4096, chunk=512, head=True,
@@ -166,7 +168,7 @@ def cpu_reference_rate(w, seconds: float, dtype: str):
         if T == 1:
             x = x[0]
         run = lambda xx: RT.score_pool(xx, w["measure"])
-    run(x[:1] if (T == 1 or w.get("head")) else x[:, :1])               # warm-up
+    run(x[:1] if T == 1 else x[:, :1])               # warm-up
     t0 = time.perf_counter()
     done = 0
     while True:
@@ -183,7 +185,8 @@ def _cpu_head_inputs(w, n_img):
     """Random-init `Final` input and kernel for the CPU legs of the fused-head workloads."""
     import torch
     g = torch.Generator().manual_seed(SEED)
-    x = torch.randn((n_img, w["H"] // 2, w["W"] // 2, 16), generator=g)
+    shape = (n_img, w["H"] // 2, w["W"] // 2, 16)
+    x = torch.randn(shape if w["T"] == 1 else (w["T"],) + shape, generator=g)
     kern = torch.from_numpy((0.4 * np.random.default_rng(SEED).standard_normal((3, 3, w["C"], 16))).astype(np.float32))
     return x, kern
 
@@ -270,8 +273,8 @@ def main():
     n_chunk_bufs = resident // chunk
     if head:
         # resident `Final`-layer inputs [chunk, H/2, W/2, 16] (random-init features and kernel, seeded)
-        if args.dtype != "f32" or T != 1:
-            raise SystemExit("the fused-head workloads are fp32, T=1")
+        if args.dtype != "f32":
+            raise SystemExit("the fused-head workloads are fp32")
         gen = torch.Generator(device=dev); gen.manual_seed(SEED + rank)
         head_kernel = (0.4 * np.random.default_rng(SEED).standard_normal((3, 3, C, 16))).astype(np.float32)
         sc.prepare_head(head_kernel)
@@ -279,6 +282,14 @@ def main():
         for i in range(n_chunk_bufs):
             f = torch.randn((chunk, H // 2, W // 2, 16), generator=gen, device=dev, dtype=torch.float32)
             f *= 0.3 + torch.rand((chunk, 1, 1, 1), generator=gen, device=dev)
+            if T > 1:
+                # T dropout forward passes: channel-wise keep masks (spatial_dropout, extra_ops.py:137-151) + noise
+                ft = torch.empty((T,) + tuple(f.shape), device=dev, dtype=torch.float32)
+                for t in range(T):
+                    keep = (torch.rand((chunk, 1, 1, 16), generator=gen, device=dev) > 0.1).float() / 0.9
+                    ft[t] = f * keep
+                    ft[t] += 0.05 * torch.randn(f.shape, generator=gen, device=dev)
+                f = ft
             bufs.append(f)
     else:
         # resident logits [T, resident, H, W, C]; chunks are dense [T, chunk, ...] tensors of their own
@@ -292,7 +303,7 @@ def main():
         nb = min(chunk, N - n0)
         buf = bufs[(n0 // chunk) % n_chunk_bufs]
         if nb < chunk and head:
-            buf = buf[:nb]
+            buf = buf[:nb] if T == 1 else buf[:, :nb].contiguous()
         elif nb < chunk:   # ragged tail: a dense [T, nb] tensor of its own
             buf = sc.synth_logits(T, id0 + n0, nb, H, W, C, dtype=dtype, seed=SEED, squeeze_t=False)
         chunks.append((buf, n0, nb))
@@ -363,14 +374,14 @@ def main():
     avg_ms = sum(m for m, _ in full) / len(full)
     bytes_launch = full[0][1] * P * (T * C * es + out_bytes_pix)
     if head:
-        bytes_launch = full[0][1] * (P // 4) * 64          # 16 fp32 channels per INPUT pixel = 16 B per output pixel
+        bytes_launch = full[0][1] * T * (P // 4) * 64      # 16 fp32 channels per INPUT pixel = 16 B per output pixel (and sample)
     peak, peak_src = load_peaks()
     achieved = bytes_launch / (avg_ms * 1e-3) / 1e9
     kernel_share = sum(a.elapsed_time(b) for a, b, _ in ev_pairs) / ms_total
 
     # ---- diagnostic: the scoring kernel alone, launched back to back on one chunk (host latency hidden) ----
     burst_buf = chunks[0][0]
-    burst_in = burst_buf if (T > 1 or head) else burst_buf[0]
+    burst_in = burst_buf if (T > 1 or head) else burst_buf[0]     # (fused-head buffers are [N,..] at T = 1 already)
     burst_out = torch.empty(chunks[0][2], dtype=torch.float64, device=dev)
     n_burst = max(4, min(40, int(0.25 / max(avg_ms * 1e-3, 1e-5))))
     burst_fn = (lambda: sc.score_features(burst_in, measure, out=burst_out)) if head else \
@@ -394,13 +405,13 @@ def main():
     e2e = None
     if not args.no_e2e and not maps:
         from semanticsegmentationactivelearning_b200 import rank_confidence
-        per_img = (P // 4) * 64 if head else T * P * C * es
+        per_img = T * (P // 4) * 64 if head else T * P * C * es
         bsz = max(1, min(8, int((2 << 30) // per_img)))              # images per sess.run-like batch (<= 8, :689)
         n_e2e = max(bsz, min(N, int((8 << 30) // per_img) // bsz * bsz))   # ~8 GB of logits per step
         tdt = torch.float32 if args.dtype == "f32" else torch.bfloat16
         if head:
-            host = torch.empty((bsz, H // 2, W // 2, 16), dtype=tdt).pin_memory()
-            host.copy_(bufs[0][:bsz])
+            host = torch.empty((bsz, H // 2, W // 2, 16) if T == 1 else (T, bsz, H // 2, W // 2, 16), dtype=tdt).pin_memory()
+            host.copy_(bufs[0][:bsz] if T == 1 else bufs[0][:, :bsz])
         else:
             host = torch.empty((T, bsz, H, W, C), dtype=tdt).pin_memory()
             host.copy_(bufs[0][:, :bsz])
@@ -439,8 +450,9 @@ def main():
             rate, cores, sample = cpu_reference_rate(w, args.cpu_seconds, dtype)
             cpu = {"value": rate / 1e9, "unit": "Gpix/s", "cores": cores, "kind": "port", "sample": sample}
         if head:
-            desc = {"kernel": "score_head_kernel<%s> C=%d: tcgen05 split-TF32 UMMA 128xNx8 + TMEM epilogue" % (measure, C),
-                    "grid": 148, "block": 640, "smem_bytes": None, "stages": 4, "tile_pixels": 512}
+            desc = {"kernel": "score_head_kernel<%s> C=%d: tcgen05 split-TF32 UMMA 128xNx8 + TMEM epilogue" % (
+                        measure if T == 1 else "multi", C),
+                    "grid": 148, "block": 704 if T == 1 else 576, "smem_bytes": None, "stages": 4, "tile_pixels": 512}
         else:
             desc = sc.describe_launch(dtype, T, chunk, H, W, C, measure)
         line = {
@@ -451,7 +463,8 @@ def main():
                        "C": C, "measure": measure, "k": K_SELECT,
                        "outputs": "scores + pseudo_confidence f32 + pseudo_label u8 + pseudo_mask u8" if maps else "scores",
                        "resident_images": resident, "chunk_images": chunk,
-                       "l2": "inputs larger than L2 (resident set %.1f GB, aliased over the pool)" % (resident * T * P * C * es / 1e9),
+                       "l2": "inputs larger than L2 (resident set %.1f GB, aliased over the pool)" % (
+                           resident * T * ((P // 4) * 64 if head else P * C * es) / 1e9),
                        "kernel": desc},
             "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches * world),
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
@@ -470,9 +483,13 @@ def main():
             line["roofline"]["limiter"] = ("SM issue slots + MUFU (19 ex2 + lg2 + rcp per pixel); ncu: XU pipe 66 %, tensor pipe 59 %, "
                                            "issue 57 %, DRAM 23 % (profiles/r01_ncu_full_cfg1h.txt)")
             line["roofline"]["tensor"] = {"kind": "tf32, 3-product split (hi*lo + lo*hi + hi*hi)", "flops_per_pixel": fl,
-                                          "achieved_tflops": fl * chunks[0][2] * P / (avg_ms * 1e-3) / 1e12,
+                                          "achieved_tflops": fl * T * chunks[0][2] * P / (avg_ms * 1e-3) / 1e12,
                                           "nominal_peak_tflops": 1100.0}
-            line["config"]["input"] = "Final-layer input [N,%d,%d,16] fp32 + kernel [3,3,%d,16]; logits never materialised" % (H // 2, W // 2, C)
+            line["config"]["input"] = "Final-layer input [%sN,%d,%d,16] fp32 + kernel [3,3,%d,16]; logits never materialised" % (
+                "" if T == 1 else "T=%d," % T, H // 2, W // 2, C)
+            if T > 1:
+                line["roofline"]["limiter"] = ("MUFU + issue slots in the Welford epilogue (T x (19 ex2 + rcp) per pixel) and the "
+                                               "loader warps (two feature rows per accumulator); not HBM bound")
         print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()

@@ -149,22 +149,24 @@ ALS_API int als_head_prepare(als_ctx* ctx, const float* kernel, int64_t C);
 ALS_API int als_head_geometry(int64_t C, int32_t* geom14, int32_t* rows);
 ALS_API int als_head_pack_weights(const float* kernel, int64_t C, float* out, int64_t out_floats);
 
-/* 1 if a fused-head kernel exists for (C, measure), else 0. */
-ALS_API int als_head_supported(int64_t C, int measure);
+/* 1 if a fused-head kernel exists for (C, measure, T samples), else 0: 2 <= C <= 32 for T == 1,
+ * 2 <= C <= 24 for T >= 2 (the per-class Welford state of a pixel pair has to fit the register file). */
+ALS_API int als_head_supported(int64_t C, int measure, int64_t T);
 
 /*
  * Score N images from their `Final`-layer input.
- *   features   device f32 [N,h,w,16], dense NHWC, 16-byte aligned
+ *   features   device f32 [T,N,h,w,16] (T == 1: [N,h,w,16]), dense NHWC, 16-byte aligned; T > 1 = the layer's
+ *              input under T Monte-Carlo-dropout forward passes (sample outermost, like the logits of als_score)
  *   scores     device f64[N]; conf_map / label / mask: optional device [N,2h,2w] as in als_score
- * Same results as als_score on conv2d_transpose(features, kernel) (to fp32 rounding).
+ * Same results as als_score on conv2d_transpose(features[t], kernel), t = 0..T-1 (to fp32 rounding).
  * Asynchronous on `stream`.
  */
-ALS_API int als_score_features(als_ctx* ctx, const void* features, int64_t N, int64_t h, int64_t w, int measure,
-                       double* scores, float* conf_map, uint8_t* label, uint8_t* mask, float threshold,
+ALS_API int als_score_features(als_ctx* ctx, const void* features, int64_t T, int64_t N, int64_t h, int64_t w,
+                       int measure, double* scores, float* conf_map, uint8_t* label, uint8_t* mask, float threshold,
                        void* stream);
 
-/* :697-700 with the fused head: like als_pool_score_batch, from the `Final`-layer input (device or host). */
-ALS_API int als_pool_score_features_batch(als_ctx* ctx, const void* features, int features_on_host, int64_t B,
+/* :697-700 with the fused head: like als_pool_score_batch, from the `Final`-layer input [T,B,h,w,16] (device or host). */
+ALS_API int als_pool_score_features_batch(als_ctx* ctx, const void* features, int features_on_host, int64_t T, int64_t B,
                                   int64_t h, int64_t w, int measure, const int64_t* example_index);
 
 /* ---- loop-level boundary (replaces rank_confidence, active_learning.py:682-715) ---- */

@@ -63,7 +63,10 @@ def _measure(prob: torch.Tensor, measure: str, C: int) -> torch.Tensor:
 def final_head(features: torch.Tensor, kernel: torch.Tensor) -> torch.Tensor:
     """`Final.call` (models/enet/enet_modules.py:1359-1381): tf.nn.conv2d_transpose(features [N,h,w,16],
     kernel [3,3,C,16], output [N,2h,2w,C], strides 2, padding SAME).  torch's conv_transpose2d without padding
-    yields the full (2h+1) x (2w+1) result; TF's SAME padding drops the last row and column."""
+    yields the full (2h+1) x (2w+1) result; TF's SAME padding drops the last row and column.
+    [T,N,h,w,16] (T Monte-Carlo forward passes, repo extension) runs the layer once per sample."""
+    if features.dim() == 5:
+        return torch.stack([final_head(features[t], kernel) for t in range(features.shape[0])])
     n, h, w, _ = features.shape
     wt = kernel.permute(3, 2, 0, 1).contiguous()                 # [in, out, kh, kw]
     full = torch.nn.functional.conv_transpose2d(features.permute(0, 3, 1, 2), wt, stride=2)

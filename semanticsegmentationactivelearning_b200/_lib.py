@@ -37,9 +37,9 @@ SIGNATURES = {
     "als_head_prepare": (C.c_int, [_p, _p, _i64]),
     "als_head_geometry": (C.c_int, [_i64, _p, _p]),
     "als_head_pack_weights": (C.c_int, [_p, _i64, _p, _i64]),
-    "als_head_supported": (C.c_int, [_i64, C.c_int]),
-    "als_score_features": (C.c_int, [_p, _p, _i64, _i64, _i64, C.c_int, _p, _p, _p, _p, C.c_float, _p]),
-    "als_pool_score_features_batch": (C.c_int, [_p, _p, C.c_int, _i64, _i64, _i64, C.c_int, _p]),
+    "als_head_supported": (C.c_int, [_i64, C.c_int, _i64]),
+    "als_score_features": (C.c_int, [_p, _p, _i64, _i64, _i64, _i64, C.c_int, _p, _p, _p, _p, C.c_float, _p]),
+    "als_pool_score_features_batch": (C.c_int, [_p, _p, C.c_int, _i64, _i64, _i64, _i64, C.c_int, _p]),
     "als_pool_begin": (C.c_int, [_p, _i64]),
     "als_pool_score_batch": (C.c_int, [_p, _p, C.c_int, C.c_int, _i64, _i64, _i64, _i64, _i64, C.c_int, _p]),
     "als_pool_scores": (C.c_int, [_p, _p, _i64]),

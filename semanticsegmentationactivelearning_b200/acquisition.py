@@ -192,9 +192,9 @@ class Scorer:
 
     # -- fused classifier head (models/enet/enet_modules.py:1294-1381 + active_learning.py:234-269) ------
     @staticmethod
-    def head_supported(num_classes: int, measure: str = "entropy") -> bool:
-        """True if a fused `Final`-head kernel is built for this class count."""
-        return bool(_lib.load().als_head_supported(int(num_classes), measure_id(measure)))
+    def head_supported(num_classes: int, measure: str = "entropy", mc_samples: int = 1) -> bool:
+        """True if a fused `Final`-head kernel is built for this class count (and MC sample count)."""
+        return bool(_lib.load().als_head_supported(int(num_classes), measure_id(measure), int(mc_samples)))
 
     def prepare_head(self, kernel) -> None:
         """Upload the `Final` layer's transposed-convolution kernel, float32 [3,3,C,16] (TF filter layout
@@ -208,27 +208,31 @@ class Scorer:
     def _features(self, features):
         torch = _torch()
         if torch is None or not isinstance(features, torch.Tensor) or not features.is_cuda:
-            raise TypeError("features must be a CUDA torch.Tensor [N,h,w,16] (host batches go through pool_score_features_batch)")
-        if features.dtype != torch.float32 or features.dim() != 4 or features.shape[-1] != 16 or not features.is_contiguous():
-            raise ValueError("features must be a dense float32 [N,h,w,16] tensor, got %s %s" % (features.dtype, tuple(features.shape)))
-        return torch, tuple(int(v) for v in features.shape[:3])
+            raise TypeError("features must be a CUDA torch.Tensor [N,h,w,16] or [T,N,h,w,16] (host batches go through "
+                            "pool_score_features_batch)")
+        if features.dtype != torch.float32 or features.dim() not in (4, 5) or features.shape[-1] != 16 or not features.is_contiguous():
+            raise ValueError("features must be a dense float32 [N,h,w,16] / [T,N,h,w,16] tensor, got %s %s"
+                             % (features.dtype, tuple(features.shape)))
+        shp = tuple(int(v) for v in features.shape[:-1])
+        return torch, ((1,) + shp if len(shp) == 3 else shp)
 
     def score_features(self, features, measure: str = "entropy", *, out=None):
-        """pseudo_mean_confidence of the logits `Final` would produce from `features` [N,h,w,16] -- without
-        materialising them.  Returns a torch.float64 CUDA tensor [N] (asynchronous)."""
+        """pseudo_mean_confidence of the logits `Final` would produce from `features` [N,h,w,16] (or the T
+        Monte-Carlo samples [T,N,h,w,16]) -- without materialising them.  Returns a torch.float64 CUDA tensor [N]
+        (asynchronous)."""
         m = measure_id(measure)
-        torch, (n, h, w) = self._features(features)
+        torch, (t, n, h, w) = self._features(features)
         if out is None:
             out = torch.empty(n, dtype=torch.float64, device=features.device)
         stream = torch.cuda.current_stream(features.device).cuda_stream
-        self._check(self._lib.als_score_features(self._ctx, features.data_ptr(), n, h, w, m, out.data_ptr(), None, None, None,
-                                                 0.0, C.c_void_p(stream)))
+        self._check(self._lib.als_score_features(self._ctx, features.data_ptr(), t, n, h, w, m, out.data_ptr(), None, None,
+                                                 None, 0.0, C.c_void_p(stream)))
         return out
 
     def pseudo_annotation_features(self, features, measure: str = "entropy", threshold: float = 0.9):
         """The PseudoAnnotation scope from the `Final`-layer input: dict like pseudo_annotation(), maps are [N,2h,2w]."""
         m = measure_id(measure)
-        torch, (n, h, w) = self._features(features)
+        torch, (t, n, h, w) = self._features(features)
         dev = features.device
         shp = (n, 2 * h, 2 * w)
         conf = torch.empty(shp, dtype=torch.float32, device=dev)
@@ -236,12 +240,14 @@ class Scorer:
         mask = torch.empty(shp, dtype=torch.uint8, device=dev)
         scores = torch.empty(n, dtype=torch.float64, device=dev)
         stream = torch.cuda.current_stream(dev).cuda_stream
-        self._check(self._lib.als_score_features(self._ctx, features.data_ptr(), n, h, w, m, scores.data_ptr(), conf.data_ptr(),
-                                                 label.data_ptr(), mask.data_ptr(), float(threshold), C.c_void_p(stream)))
+        self._check(self._lib.als_score_features(self._ctx, features.data_ptr(), t, n, h, w, m, scores.data_ptr(),
+                                                 conf.data_ptr(), label.data_ptr(), mask.data_ptr(), float(threshold),
+                                                 C.c_void_p(stream)))
         return {"pseudo_confidence": conf, "pseudo_mean_confidence": scores, "pseudo_label": label, "pseudo_mask": mask}
 
     def pool_score_features_batch(self, features, batch_indices, measure: str = "entropy") -> None:
-        """pool_score_batch from the `Final`-layer input [B,h,w,16] (CUDA tensor, or host tensor / array: staged)."""
+        """pool_score_batch from the `Final`-layer input [B,h,w,16] or [T,B,h,w,16] (CUDA tensor, or host tensor /
+        array: staged)."""
         m = measure_id(measure)
         torch = _torch()
         if torch is not None and isinstance(features, torch.Tensor):
@@ -254,14 +260,15 @@ class Scorer:
             ptr, on_host, shape = features.ctypes.data, True, features.shape
         else:
             raise TypeError("features must be a torch.Tensor or numpy.ndarray")
-        if len(shape) != 4 or shape[-1] != 16:
-            raise ValueError("features must be [B,h,w,16], got %s" % (tuple(shape),))
+        if len(shape) not in (4, 5) or shape[-1] != 16:
+            raise ValueError("features must be [B,h,w,16] or [T,B,h,w,16], got %s" % (tuple(shape),))
+        t, b, h, w = ((1,) + tuple(shape[:3])) if len(shape) == 4 else tuple(shape[:4])
         idx = np.ascontiguousarray(np.asarray(batch_indices, dtype=np.int64))
-        if idx.shape != (shape[0],):
-            raise ValueError("batch_indices must have one entry per image (%d), got shape %s" % (shape[0], idx.shape))
+        if idx.shape != (b,):
+            raise ValueError("batch_indices must have one entry per image (%d), got shape %s" % (b, idx.shape))
         self._keep = features
-        self._check(self._lib.als_pool_score_features_batch(self._ctx, ptr, 1 if on_host else 0, int(shape[0]), int(shape[1]),
-                                                            int(shape[2]), m, idx.ctypes.data))
+        self._check(self._lib.als_pool_score_features_batch(self._ctx, ptr, 1 if on_host else 0, int(t), int(b), int(h),
+                                                            int(w), m, idx.ctypes.data))
 
     def score_dlpack(self, producer, measure: str = "entropy") -> np.ndarray:
         """Score any ``__dlpack__`` producer (TF >= 2.2, CuPy, JAX, NumPy, torch): device tensors

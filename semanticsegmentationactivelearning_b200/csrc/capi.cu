@@ -520,14 +520,16 @@ int als_score_dlpack(als_ctx* ctx, void* managed, int measure, double* scores) {
 
 namespace {
 
-int check_features(als_ctx* ctx, const void* features, int64_t N, int64_t h, int64_t w, int measure, bool want_label) {
+int check_features(als_ctx* ctx, const void* features, int64_t T, int64_t N, int64_t h, int64_t w, int measure, bool want_label) {
   if (!ctx) return fail(nullptr, ALS_ERR_INVALID, "context is NULL");
   if (measure < ALS_ENTROPY || measure > ALS_VARIANCE)
     return fail(ctx, ALS_ERR_UNSUPPORTED, "Uncertainty function not implemented.");
   if (ctx->head_C <= 0) return fail(ctx, ALS_ERR_STATE, "als_head_prepare has not been called");
-  if (measure == ALS_VARIANCE) return fail(ctx, ALS_ERR_INVALID, "measure 'variance' needs T >= 2 Monte-Carlo samples");
-  if (!als_head_supported(ctx->head_C, measure))
-    return fail(ctx, ALS_ERR_UNSUPPORTED, "no fused-head kernel for C=%lld", (long long)ctx->head_C);
+  if (T < 1 || T > 4096) return fail(ctx, ALS_ERR_INVALID, "bad sample count T=%lld", (long long)T);
+  if (measure == ALS_VARIANCE && T < 2) return fail(ctx, ALS_ERR_INVALID, "measure 'variance' needs T >= 2 Monte-Carlo samples");
+  if (!als_head_supported(ctx->head_C, measure, T))
+    return fail(ctx, ALS_ERR_UNSUPPORTED, "no fused-head kernel for C=%lld with T=%lld (use als_score on the logits)",
+                (long long)ctx->head_C, (long long)T);
   if (N < 0 || h < 1 || w < 1) return fail(ctx, ALS_ERR_INVALID, "bad feature shape [N=%lld,h=%lld,w=%lld,16]", (long long)N, (long long)h, (long long)w);
   if (h > (1 << 20) || w > (1 << 20) || N > 0x7fffffff) return fail(ctx, ALS_ERR_INVALID, "feature map too large");
   if (want_label && ctx->head_C > 256) return fail(ctx, ALS_ERR_INVALID, "uint8 pseudo_label needs C <= 256");
@@ -536,14 +538,14 @@ int check_features(als_ctx* ctx, const void* features, int64_t N, int64_t h, int
   return ALS_OK;
 }
 
-// device features [N,h,w,16] -> fixed-point sums -> finalize (scores64 and/or pool scatter)
-int score_features_device(als_ctx* ctx, const void* features, int64_t N, int64_t h, int64_t w, int measure, double* scores64,
+// device features [T,N,h,w,16] -> fixed-point sums -> finalize (scores64 and/or pool scatter)
+int score_features_device(als_ctx* ctx, const void* features, int64_t T, int64_t N, int64_t h, int64_t w, int measure, double* scores64,
                           float* pool32, const long long* example_index_dev, int64_t num_examples, float* conf_map,
                           uint8_t* label, uint8_t* mask, float threshold, cudaStream_t stream) {
   if (N == 0) return ALS_OK;
   const int C = static_cast<int>(ctx->head_C);
-  als::HeadPlan plan = als::plan_head(C, measure, ctx->num_sms);
-  if (!plan.func) return fail(ctx, ALS_ERR_UNSUPPORTED, "no fused-head kernel for C=%d", C);
+  als::HeadPlan plan = als::plan_head(C, measure, static_cast<int>(T), ctx->num_sms);
+  if (!plan.func) return fail(ctx, ALS_ERR_UNSUPPORTED, "no fused-head kernel for C=%d, T=%lld", C, (long long)T);
   if (plan.smem_bytes > ctx->max_smem) return fail(ctx, ALS_ERR_CUDA, "fused head needs %d bytes of shared memory", plan.smem_bytes);
   const long long P = 4ll * h * w;  // output pixels per image (2h x 2w)
   int shift = 62 - ceil_log2_ll(P);
@@ -551,12 +553,12 @@ int score_features_device(als_ctx* ctx, const void* features, int64_t N, int64_t
   als::HeadParams p{};
   p.sp.P = P;
   p.sp.total_pixels = N * P;
-  p.sp.T = 1;
+  p.sp.T = static_cast<int>(T);
   p.sp.C = C;
   p.sp.measure = measure;
   p.sp.inv_log2_c = static_cast<float>(1.0 / log2(static_cast<double>(C)));
   p.sp.threshold = threshold;
-  p.sp.inv_T = 1.0f;
+  p.sp.inv_T = 1.0f / static_cast<float>(T);
   p.sp.fx_scale = ldexpf(1.0f, shift);
   p.sp.acc = ctx->acc;
   p.sp.acc_stride = ctx->acc_cap;
@@ -566,12 +568,15 @@ int score_features_device(als_ctx* ctx, const void* features, int64_t N, int64_t
   p.sp.label = label;
   p.sp.mask = mask;
   p.features = static_cast<const float*>(features);
+  p.sample_stride = N * h * w * als::kHeadChannels;
+  p.T = static_cast<int>(T);
   p.weights = ctx->head_weights;
   p.h = static_cast<int>(h);
   p.w = static_cast<int>(w);
   p.n_images = static_cast<int>(N);
   p.n_strips = static_cast<int>((w + als::kHeadTileQuads - 1) / als::kHeadTileQuads);
   // rows per unit: about 12 units per SM, 8..64 rows (one halo row is re-read per unit), evenly split
+  // (T > 1: every tile brings its own rows, a unit is T times the work: aim for the same unit count)
   long long r = (N * h * p.n_strips) / (12ll * ctx->num_sms);
   if (r < 8) r = 8;
   if (r > 64) r = 64;
@@ -593,9 +598,9 @@ int score_features_device(als_ctx* ctx, const void* features, int64_t N, int64_t
 
 extern "C" {
 
-int als_head_supported(int64_t C, int measure) {
-  if (C < 2 || C > 32) return 0;
-  return als::plan_head(static_cast<int>(C), measure, 1).func != nullptr ? 1 : 0;
+int als_head_supported(int64_t C, int measure, int64_t T) {
+  if (C < 2 || C > als::kHeadMaxClasses || T < 1 || T > 4096) return 0;
+  return als::plan_head(static_cast<int>(C), measure, static_cast<int>(T), 1).func != nullptr ? 1 : 0;
 }
 
 int als_head_geometry(int64_t C, int32_t* geom14, int32_t* rows) {
@@ -626,7 +631,7 @@ int als_head_prepare(als_ctx* ctx, const float* kernel, int64_t C) {
   if (!ctx) return fail(nullptr, ALS_ERR_INVALID, "context is NULL");
   if (!kernel) return fail(ctx, ALS_ERR_INVALID, "kernel pointer is NULL");
   if (C < 2) return fail(ctx, ALS_ERR_INVALID, "need at least 2 classes, got C=%lld", (long long)C);
-  if (!als_head_supported(C, ALS_ENTROPY))
+  if (!als_head_supported(C, ALS_ENTROPY, 1))
     return fail(ctx, ALS_ERR_UNSUPPORTED, "no fused-head kernel is built for C=%lld (use als_score on the logits)", (long long)C);
   DeviceGuard g(ctx->device);
   const als::HeadGeom geom = als::head_geometry(static_cast<int>(C));
@@ -643,9 +648,9 @@ int als_head_prepare(als_ctx* ctx, const float* kernel, int64_t C) {
   return ALS_OK;
 }
 
-int als_score_features(als_ctx* ctx, const void* features, int64_t N, int64_t h, int64_t w, int measure, double* scores,
+int als_score_features(als_ctx* ctx, const void* features, int64_t T, int64_t N, int64_t h, int64_t w, int measure, double* scores,
                        float* conf_map, uint8_t* label, uint8_t* mask, float threshold, void* stream) {
-  ALS_TRY(check_features(ctx, features, N, h, w, measure, label != nullptr));
+  ALS_TRY(check_features(ctx, features, T, N, h, w, measure, label != nullptr));
   if (N == 0) return ALS_OK;
   if (!scores) return fail(ctx, ALS_ERR_INVALID, "scores pointer is NULL");
   DeviceGuard g(ctx->device);
@@ -656,12 +661,12 @@ int als_score_features(als_ctx* ctx, const void* features, int64_t N, int64_t h,
   ALS_TRY(check_device_ptr(ctx, mask, "mask"));
   ALS_TRY(ensure_acc(ctx, N));
   cudaStream_t st = stream ? static_cast<cudaStream_t>(stream) : ctx->stream;
-  return score_features_device(ctx, features, N, h, w, measure, scores, nullptr, nullptr, 0, conf_map, label, mask, threshold, st);
+  return score_features_device(ctx, features, T, N, h, w, measure, scores, nullptr, nullptr, 0, conf_map, label, mask, threshold, st);
 }
 
-int als_pool_score_features_batch(als_ctx* ctx, const void* features, int features_on_host, int64_t B, int64_t h, int64_t w,
-                                  int measure, const int64_t* example_index) {
-  ALS_TRY(check_features(ctx, features, B, h, w, measure, false));
+int als_pool_score_features_batch(als_ctx* ctx, const void* features, int features_on_host, int64_t T, int64_t B, int64_t h,
+                                  int64_t w, int measure, const int64_t* example_index) {
+  ALS_TRY(check_features(ctx, features, T, B, h, w, measure, false));
   if (ctx->pool_n < 0) return fail(ctx, ALS_ERR_STATE, "als_pool_begin has not been called");
   if (B == 0) return ALS_OK;
   if (!example_index) return fail(ctx, ALS_ERR_INVALID, "example_index is NULL");
@@ -675,7 +680,7 @@ int als_pool_score_features_batch(als_ctx* ctx, const void* features, int featur
   const void* dev = features;
   int b = -1;
   if (features_on_host) {
-    const Shape s{1, B, h, w, als::kHeadChannels};
+    const Shape s{T, B, h, w, als::kHeadChannels};
     ALS_TRY(ensure_stage(ctx, static_cast<size_t>(s.elems()) * 4));
     ALS_TRY(stage_chunk(ctx, static_cast<const unsigned char*>(features), s, 4, 0, B, &b));
     ALS_CUDA(ctx, cudaStreamWaitEvent(ctx->stream, ctx->ev_copied[b], 0));
@@ -685,7 +690,7 @@ int als_pool_score_features_batch(als_ctx* ctx, const void* features, int featur
   }
   ALS_CUDA(ctx, cudaMemcpyAsync(ctx->index_dev, example_index, static_cast<size_t>(B) * sizeof(int64_t),
                                 cudaMemcpyHostToDevice, ctx->stream));
-  ALS_TRY(score_features_device(ctx, dev, B, h, w, measure, nullptr, ctx->pool32, ctx->index_dev, ctx->pool_n, nullptr, nullptr,
+  ALS_TRY(score_features_device(ctx, dev, T, B, h, w, measure, nullptr, ctx->pool32, ctx->index_dev, ctx->pool_n, nullptr, nullptr,
                                 nullptr, 0.f, ctx->stream));
   if (b >= 0) {
     ALS_CUDA(ctx, cudaEventRecord(ctx->ev_scored[b], ctx->stream));

@@ -104,8 +104,15 @@ __host__ __device__ constexpr int cmax(int a, int b) { return a > b ? a : b; }
 
 // Compile-time twin of head_geometry(C) (the host packs the weights with the run-time one; a static_assert-free
 // consistency check runs in plan_head).
-template <int C>
+//
+// EPB = accumulator blocks (quad pixels) one epilogue warp owns.  4: single sample -- a warp serves ONE accumulator
+// stage and all four blocks of its lane quarter.  2 or 1: Monte-Carlo samples (T > 1) -- the per-class Welford state
+// of four pixels does not fit one thread, so the blocks are split over 16 / EPB warps that all work on the SAME
+// accumulator and keep the state of their EPB pixels in registers across the T samples of a tile.
+template <int C, int EPB = 4>
 struct Geom {
+  static_assert(EPB == 4 || EPB == 2 || EPB == 1, "blocks per epilogue warp");
+  static constexpr bool MULTI = EPB < 4;
   static constexpr int CB = cround(C, 4);
   static constexpr int N1 = cround(2 * CB, 16), N2 = cround(2 * CB, 16), N3 = cround(CB, 16);
   static constexpr int N0 = cround(cmax(4 * CB, cmax(N1, cmax(CB + N2, CB + N3))), 16);  // also initialises every column
@@ -116,10 +123,12 @@ struct Geom {
   static_assert(A_COL0 + kARing * kARowCols <= kTmemCols, "tensor memory budget");
   // Warp roles by warp id.  The SM's issue arbiter favours HIGHER warp ids, so the roles on the critical path
   // (producer, MMA issuer, loaders) sit above the epilogue warps, which mostly wait.
-  static constexpr int FIRST_LOADER_WARP = 4 * ACC_STAGES;  // warps below: epilogue, stage = warp >> 2, lane quarter = warp & 3
+  static constexpr int EPI_WARPS = MULTI ? 16 / EPB : 4 * ACC_STAGES;
+  static constexpr int ACC_ARRIVALS = MULTI ? EPI_WARPS : 4;  // epilogue warps that release one accumulator stage
+  static constexpr int FIRST_LOADER_WARP = EPI_WARPS;  // warps below: epilogue, lane quarter = warp & 3 (stage or block group = warp >> 2)
   static constexpr int MMA_WARP = FIRST_LOADER_WARP + 4 * kLoaderGroups;
   static constexpr int PRODUCER_WARP = MMA_WARP + 1;
-  static constexpr int THREADS = 32 * (PRODUCER_WARP + 1);   // 704 (3 stages) or 576 (2 stages)
+  static constexpr int THREADS = 32 * (PRODUCER_WARP + 1);   // 704 (3 stages) or 576 (2 stages, or T > 1 with EPB = 2)
 };
 
 // TMEM -> registers, CNT consecutive columns (CNT multiple of 4, <= 32)
@@ -191,9 +200,11 @@ __device__ __forceinline__ void store_split(uint32_t taddr, const float4 (&v)[4]
   tc05::st16(taddr + 16, lo);
 }
 
-template <int C, int MEASURE>
-__global__ void __launch_bounds__(Geom<C>::THREADS, 1) score_head_kernel(const HeadParams p) {
-  using G = Geom<C>;
+template <int C, int MEASURE, int EPB>
+__global__ void __launch_bounds__(Geom<C, EPB>::THREADS, 1) score_head_kernel(const HeadParams p) {
+  using G = Geom<C, EPB>;
+  constexpr bool MULTI = G::MULTI;  // T > 1: every tile is computed once per Monte-Carlo sample
+  static_assert(MULTI == (MEASURE == kMulti), "T > 1 runs the kMulti instantiation (measure is a run-time field)");
   constexpr int CB = G::CB;
   constexpr int kAccStages = G::ACC_STAGES;
   constexpr int kAccStride = G::N0;   // accumulator columns per stage
@@ -230,7 +241,7 @@ __global__ void __launch_bounds__(Geom<C>::THREADS, 1) score_head_kernel(const H
     }
     for (int s = 0; s < kAccStages; ++s) {
       mbar_init(&full_acc[s], 1);
-      mbar_init(&empty_acc[s], 4);
+      mbar_init(&empty_acc[s], G::ACC_ARRIVALS);
     }
     mbar_init(wbar, 1);
     fence_mbar_init();
@@ -253,17 +264,16 @@ __global__ void __launch_bounds__(Geom<C>::THREADS, 1) score_head_kernel(const H
       for (long long u = blockIdx.x; u < p.n_units; u += gridDim.x) {
         const Unit un = decode_unit(p, u);
         const int first = un.j0 == 0 ? 1 : 0;
-        for (int r = -1; r < un.rows; ++r) {
-          const int row = un.i0 + r;
+        // feature row `row` (-1 = the padding row above the image) of sample t -> next raw slot
+        auto issue_row = [&](int row, int t) {
           mbar_wait_relaxed(&empty_raw[s], ph ^ 1u);
-          if (r >= 0) { ALS_TRACE(ptile, 7); ++ptile; }
           meta[s].valid = un.valid;
           meta[s].first = first;
           meta[s].zero = row < 0 ? 1 : 0;
           if (row < 0) {
             mbar_arrive_expect_tx(&full_raw[s], 0);
           } else {
-            const float* src = p.features +
+            const float* src = p.features + t * p.sample_stride +
                                ((static_cast<long long>(un.n) * p.h + row) * p.w + (un.j0 - (first ? 0 : 1))) * kHeadChannels;
             const uint32_t bytes = static_cast<uint32_t>(un.valid + (first ? 0 : 1)) * 64u;
             unsigned char* dst = raw_base + s * kRawSlotBytes + (first ? 64 : 0);
@@ -271,6 +281,22 @@ __global__ void __launch_bounds__(Geom<C>::THREADS, 1) score_head_kernel(const H
             bulk_g2s(dst, src, bytes, &full_raw[s], policy);
           }
           if (++s == kRawStages) { s = 0; ph ^= 1u; }
+        };
+        if constexpr (!MULTI) {
+          // one sample: a row is loaded once and serves the tile below it as "previous" and its own as "current"
+          for (int r = -1; r < un.rows; ++r) {
+            if (r >= 0) { ALS_TRACE(ptile, 7); ++ptile; }
+            issue_row(un.i0 + r, 0);
+          }
+        } else {
+          // T samples: the Welford state of a tile lives in the epilogue's registers, so the samples of ONE tile
+          // run back to back and every (tile, sample) brings its own previous and current row (the re-read of the
+          // previous row comes out of L2: it was the current row of the tile above, T samples ago)
+          for (int k = 0; k < un.rows; ++k)
+            for (int t = 0; t < p.T; ++t) {
+              issue_row(un.i0 + k - 1, t);
+              issue_row(un.i0 + k, t);
+            }
         }
       }
     }
@@ -291,48 +317,66 @@ __global__ void __launch_bounds__(Geom<C>::THREADS, 1) score_head_kernel(const H
     uint32_t tile = 0;  // (trace only)
     int a = 0;          // accumulator stage of the next tile and its phase
     uint32_t acc_ph = 0;
+    // the 24 MMAs of one accumulator: current row in ring slot rb_cur, the row above it in rb_prev
+    auto issue_tile = [&](int rb_prev, int rb_cur, bool release_cur) {
+      ALS_TRACE(tile, 2);
+      const uint32_t d = tmem + a * kAccStride;
+      const uint32_t a_row[2] = {tmem + kACol0 + rb_cur * kARowCols, tmem + kACol0 + rb_prev * kARowCols};
+      // The small cross terms go first and the hi*hi products last: the tensor core truncates when it adds
+      // into the accumulator, so every MMA issued after the accumulator has reached full scale costs
+      // ~2^-24 of it -- 8 such steps this way round instead of 24.
+#pragma unroll
+      for (int pc = 0; pc < 3; ++pc) {  // hi*lo, lo*hi, hi*hi
+        const uint32_t a_part = (pc == 1) ? 16 : 0;        // columns: hi 0..15, lo 16..31
+        const uint32_t b_part = (pc == 0) ? kWPart : 0;
+#pragma unroll
+        for (int o = 0; o < 4; ++o) {
+#pragma unroll
+          for (int ks = 0; ks < 2; ++ks) {
+            const uint32_t a_col = ((o < 2) ? 0u : 32u) + a_part + ks * 8;  // own pixel for sources (.,j), left for (.,j-1)
+            const uint32_t b_off = (b_part + kRow0[o] * 16 + ks * 2 * kLboB) >> 4;
+            tc05::mma_tf32_ts(d + kCol0[o], a_row[o & 1] + a_col, b_base + b_off, kIdesc[o],
+                              !(pc == 0 && o == 0 && ks == 0));
+          }
+        }
+      }
+      tc05::commit(&full_acc[a]);
+      tc05::commit(&empty_a[rb_prev]);
+      if (release_cur) tc05::commit(&empty_a[rb_cur]);
+      ALS_TRACE(tile, 3);
+    };
     for (long long u = blockIdx.x; u < p.n_units; u += gridDim.x) {
       const Unit un = decode_unit(p, u);
-      // halo row of the unit
-      mbar_wait(&full_a[seq & (kARing - 1)], (seq / kARing) & 1u);
-      for (int k = 0; k < un.rows; ++k) {
-        const uint32_t sp = seq + k, sc = seq + k + 1;
-        const int rb_prev = sp & (kARing - 1), rb_cur = sc & (kARing - 1);
-        mbar_wait(&full_a[rb_cur], (sc / kARing) & 1u);
-        mbar_wait(&empty_acc[a], acc_ph ^ 1u);
-        tc05::fence_after_sync();
-        if (leader) {
-          ALS_TRACE(tile, 2);
-          const uint32_t d = tmem + a * kAccStride;
-          const uint32_t a_row[2] = {tmem + kACol0 + rb_cur * kARowCols, tmem + kACol0 + rb_prev * kARowCols};
-          // The small cross terms go first and the hi*hi products last: the tensor core truncates when it adds
-          // into the accumulator, so every MMA issued after the accumulator has reached full scale costs
-          // ~2^-24 of it -- 8 such steps this way round instead of 24.
-#pragma unroll
-          for (int pc = 0; pc < 3; ++pc) {  // hi*lo, lo*hi, hi*hi
-            const uint32_t a_part = (pc == 1) ? 16 : 0;        // columns: hi 0..15, lo 16..31
-            const uint32_t b_part = (pc == 0) ? kWPart : 0;
-#pragma unroll
-            for (int o = 0; o < 4; ++o) {
-#pragma unroll
-              for (int ks = 0; ks < 2; ++ks) {
-                const uint32_t a_col = ((o < 2) ? 0u : 32u) + a_part + ks * 8;  // own pixel for sources (.,j), left for (.,j-1)
-                const uint32_t b_off = (b_part + kRow0[o] * 16 + ks * 2 * kLboB) >> 4;
-                tc05::mma_tf32_ts(d + kCol0[o], a_row[o & 1] + a_col, b_base + b_off, kIdesc[o],
-                                  !(pc == 0 && o == 0 && ks == 0));
-              }
-            }
-          }
-          tc05::commit(&full_acc[a]);
-          tc05::commit(&empty_a[rb_prev]);
-          if (k == un.rows - 1) tc05::commit(&empty_a[rb_cur]);
-          ALS_TRACE(tile, 3);
+      if constexpr (!MULTI) {
+        // halo row of the unit
+        mbar_wait(&full_a[seq & (kARing - 1)], (seq / kARing) & 1u);
+        for (int k = 0; k < un.rows; ++k) {
+          const uint32_t sp = seq + k, sc = seq + k + 1;
+          const int rb_prev = sp & (kARing - 1), rb_cur = sc & (kARing - 1);
+          mbar_wait(&full_a[rb_cur], (sc / kARing) & 1u);
+          mbar_wait(&empty_acc[a], acc_ph ^ 1u);
+          tc05::fence_after_sync();
+          if (leader) issue_tile(rb_prev, rb_cur, k == un.rows - 1);
+          __syncwarp();
+          ++tile;
+          if (++a == kAccStages) { a = 0; acc_ph ^= 1u; }
         }
-        __syncwarp();
-        ++tile;
-        if (++a == kAccStages) { a = 0; acc_ph ^= 1u; }
+        seq += un.rows + 1;
+      } else {
+        // T > 1: one accumulator per (tile, sample), each with its own pair of rows
+        const int n_acc = un.rows * p.T;
+        for (int q = 0; q < n_acc; ++q, seq += 2) {
+          const int rb_prev = seq & (kARing - 1), rb_cur = (seq + 1) & (kARing - 1);
+          mbar_wait(&full_a[rb_prev], (seq / kARing) & 1u);
+          mbar_wait(&full_a[rb_cur], ((seq + 1) / kARing) & 1u);
+          mbar_wait(&empty_acc[a], acc_ph ^ 1u);
+          tc05::fence_after_sync();
+          if (leader) issue_tile(rb_prev, rb_cur, true);
+          __syncwarp();
+          ++tile;
+          if (++a == kAccStages) { a = 0; acc_ph ^= 1u; }
+        }
       }
-      seq += un.rows + 1;
     }
   } else if (warp >= kFirstLoaderWarp) {
     // ===== loaders: raw NHWC row -> chunk planes (shared) -> hi / lo A rows in tensor memory =====
@@ -348,7 +392,9 @@ __global__ void __launch_bounds__(Geom<C>::THREADS, 1) score_head_kernel(const H
     uint32_t stile = 0;   // (trace only)
     for (long long u = blockIdx.x; u < p.n_units; u += gridDim.x) {
       const Unit un = decode_unit(p, u);
-      for (int r = -1; r < un.rows; ++r, ++rs) {
+      const int n_rows = MULTI ? 2 * un.rows * p.T : un.rows + 1;  // feature rows the producer sends for this unit
+      for (int vr = 0; vr < n_rows; ++vr, ++rs) {
+        const int r = vr - 1;  // (trace only; single sample: row inside the unit)
         if (r >= 0) ++stile;
         const int s_row = s;
         const uint32_t phs_row = phs;
@@ -395,8 +441,8 @@ __global__ void __launch_bounds__(Geom<C>::THREADS, 1) score_head_kernel(const H
         if (r >= 0 && lt == 0) ALS_TRACE(stile - 1, 1);
       }
     }
-  } else {
-    // ===== epilogue: tensor memory -> confidences -> per-image sums =====
+  } else if constexpr (!MULTI) {
+    // ===== epilogue, one sample: tensor memory -> confidences -> per-image sums =====
     const int e = warp - kFirstEpilogueWarp;
     const int a = e >> 2;          // accumulator stage this warp serves
     const int quarter = warp & 3;  // TMEM lane quarter this warp may read
@@ -457,6 +503,78 @@ __global__ void __launch_bounds__(Geom<C>::THREADS, 1) score_head_kernel(const H
               const long long g = (static_cast<long long>(un.n) * (2 * p.h) + (2 * i + dy)) * W + 2 * (un.j0 + m) + dx;
               if (sp.conf_map) sp.conf_map[g] = conf[b];
               if (sp.mask) sp.mask[g] = (conf[b] < sp.threshold) ? 0 : 1;  // active_learning.py:265-269
+              if (sp.label) sp.label[g] = static_cast<uint8_t>(lbl[b]);
+            }
+          }
+        }
+      }
+    }
+    acc.flush(sp);
+  } else {
+    // ===== epilogue, T samples: every warp takes its EPB blocks of EVERY accumulator; the running mean of the
+    // softmax (per class) and the summed M2 of its pixels stay in registers over the T samples of a tile =====
+    const int quarter = warp & 3;             // TMEM lane quarter this warp may read
+    const int blk0 = (warp >> 2) * EPB;       // first accumulator block (quad pixel) of this warp
+    const int m = quarter * 32 + lane;
+    const uint32_t tbase = tmem + (static_cast<uint32_t>(quarter * 32) << 16) + blk0 * CB;
+    const ScoreParams& sp = p.sp;
+    const int W = 2 * p.w;
+    ImageAcc acc;
+    int a = 0;           // accumulator stage of the next (tile, sample) and its phase
+    uint32_t ph = 0;
+    for (long long u = blockIdx.x; u < p.n_units; u += gridDim.x) {
+      const Unit un = decode_unit(p, u);
+      if (un.n != acc.img) {
+        acc.flush(sp);
+        acc.img = un.n;
+      }
+      const bool valid = m < un.valid;
+      for (int k = 0; k < un.rows; ++k) {
+        float nmu[EPB][C];  // negated running mean of the class probabilities (pixel_math.cuh: welford_update)
+        float m2s[EPB];
+        int lbl[EPB];
+#pragma unroll
+        for (int b = 0; b < EPB; ++b) {
+          m2s[b] = 0.f;
+          lbl[b] = 0;
+#pragma unroll
+          for (int j = 0; j < C; ++j) nmu[b][j] = 0.f;
+        }
+        for (int t = 0; t < p.T; ++t) {
+          mbar_wait_relaxed(&full_acc[a], ph);
+          tc05::fence_after_sync();
+          const float inv_t = __frcp_rn(static_cast<float>(t + 1));
+          const uint32_t tacc = tbase + a * kAccStride;
+#pragma unroll
+          for (int b = 0; b < EPB; ++b) {
+            float v[CB];
+            ld_cols<CB>(tacc + b * CB, v);
+            tc05::ld_wait();
+            if (b == EPB - 1) {  // this warp's share is in registers
+              tc05::fence_before_sync();
+              __syncwarp();
+              if (lane == 0) mbar_arrive(&empty_acc[a]);
+            }
+            float x[C];
+#pragma unroll
+            for (int j = 0; j < C; ++j) x[j] = v[j];
+            if (t == 0 && sp.label) lbl[b] = group_argmax<C, 1>(x, C, 0);  // pseudo_label of sample 0, as in score.cu
+            welford_update<C, 1, true>(x, C, inv_t, nmu[b], m2s[b]);
+          }
+          if (++a == kAccStages) { a = 0; ph ^= 1u; }
+        }
+        if (valid) {
+          const int i = un.i0 + k;
+#pragma unroll
+          for (int b = 0; b < EPB; ++b) {
+            const float conf = conf_multi<C, 1, true>(nmu[b], m2s[b], C, sp);
+            acc.add(conf, sp.fx_scale);
+            if (sp.any_out) {
+              const int blk = blk0 + b;
+              const int dy = blk >> 1, dx = (blk == 0 || blk == 3) ? 1 : 0;  // blocks: (0,1) (0,0) (1,0) (1,1)
+              const long long g = (static_cast<long long>(un.n) * (2 * p.h) + (2 * i + dy)) * W + 2 * (un.j0 + m) + dx;
+              if (sp.conf_map) sp.conf_map[g] = conf;
+              if (sp.mask) sp.mask[g] = (conf < sp.threshold) ? 0 : 1;  // active_learning.py:265-269
               if (sp.label) sp.label[g] = static_cast<uint8_t>(lbl[b]);
             }
           }
@@ -534,12 +652,26 @@ size_t pack_head_weights(const float* kernel, int C, float* out) {
   return 2 * part;
 }
 
+// Monte-Carlo variant (T > 1): blocks per epilogue warp.  Two pixels of Welford state (2C + 2 registers) fit the
+// 112-register budget of the 576-thread CTA up to kHeadMaxClassesMC classes; above that the state would spill.
+constexpr int kEpbMulti = 2;
+
 template <int C>
-static const void* pick_head(int measure, const char** name) {
+static const void* pick_head(int measure, int T, const char** name, int* block) {
+  if (T > 1) {
+    if constexpr (C <= kHeadMaxClassesMC) {
+      *name = "score_head_kernel<multi>";
+      *block = Geom<C, kEpbMulti>::THREADS;
+      return (const void*)score_head_kernel<C, kMulti, kEpbMulti>;
+    } else {
+      return nullptr;
+    }
+  }
+  *block = Geom<C>::THREADS;
   switch (measure) {
-    case kEntropy: *name = "score_head_kernel<entropy>"; return (const void*)score_head_kernel<C, kEntropy>;
-    case kMargin: *name = "score_head_kernel<margin>"; return (const void*)score_head_kernel<C, kMargin>;
-    case kConfidence: *name = "score_head_kernel<confidence>"; return (const void*)score_head_kernel<C, kConfidence>;
+    case kEntropy: *name = "score_head_kernel<entropy>"; return (const void*)score_head_kernel<C, kEntropy, 4>;
+    case kMargin: *name = "score_head_kernel<margin>"; return (const void*)score_head_kernel<C, kMargin, 4>;
+    case kConfidence: *name = "score_head_kernel<confidence>"; return (const void*)score_head_kernel<C, kConfidence, 4>;
     default: return nullptr;
   }
 }
@@ -556,16 +688,16 @@ static bool geometry_agrees(const HeadGeom& g) {
          g.row0[2] == T::N0 + T::N1 && g.row0[3] == T::N0 + T::N1 + T::N2;
 }
 
-HeadPlan plan_head(int C, int measure, int num_sms) {
+HeadPlan plan_head(int C, int measure, int T, int num_sms) {
   HeadPlan plan{};
   const HeadGeom g = head_geometry(C);
   bool same = false;
+  if (T < 1 || measure < kEntropy || measure > kVariance || (measure == kVariance && T < 2)) return plan;
   switch (C) {
-#define X(c)                                       \
-  case c:                                          \
-    plan.func = pick_head<c>(measure, &plan.name); \
-    plan.block = Geom<c>::THREADS;                 \
-    same = geometry_agrees<c>(g);                  \
+#define X(c)                                                       \
+  case c:                                                          \
+    plan.func = pick_head<c>(measure, T, &plan.name, &plan.block); \
+    same = geometry_agrees<c>(g);                                  \
     break;
     ALS_HEAD_C_LIST(X)
 #undef X

@@ -9,6 +9,8 @@ namespace als {
 
 constexpr int kHeadChannels = 16;   // input channels of `Final` (models/enet/enet_modules.py:1341)
 constexpr int kHeadTileQuads = 128; // input pixels per MMA tile (UMMA M)
+constexpr int kHeadMaxClasses = 32;   // fused kernels exist for 2 <= C <= 32 ...
+constexpr int kHeadMaxClassesMC = 24; // ... and, with T > 1 Monte-Carlo samples, for 2 <= C <= 24
 
 // Column layout of one accumulator tile: 4 blocks of CB = round_up(C, 4) columns, one per output pixel of
 // the 2x2 quad an input pixel produces:  block 0 -> (dy,dx) = (0,1), 1 -> (0,0), 2 -> (1,0), 3 -> (1,1).
@@ -30,7 +32,9 @@ size_t pack_head_weights(const float* kernel, int C, float* out);
 
 struct HeadParams {
   ScoreParams sp;          // P = H*W of the OUTPUT (2h x 2w); acc / flags / outputs / fx_scale as in score.cu
-  const float* features;   // [N][h][w][16] fp32, 16-byte aligned
+  const float* features;   // [T][N][h][w][16] fp32, 16-byte aligned
+  long long sample_stride; // elements between Monte-Carlo samples = N*h*w*16
+  int T;                   // samples (1 = the reference's single forward pass)
   const float* weights;    // packed B image (pack_head_weights), device
   int h, w;                // input (feature) height / width; output is 2h x 2w
   int n_images;
@@ -47,8 +51,8 @@ struct HeadPlan {
   int grid, block, smem_bytes;
 };
 
-// nullptr func when (C, measure) has no fused-head instantiation.
-HeadPlan plan_head(int C, int measure, int num_sms);
+// nullptr func when (C, measure, T) has no fused-head instantiation.
+HeadPlan plan_head(int C, int measure, int T, int num_sms);
 cudaError_t launch_head(const HeadPlan& plan, HeadParams p, cudaStream_t stream);
 
 }  // namespace als
