@@ -6,7 +6,10 @@ import ctypes as C
 import os
 
 PKG = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(PKG, "libalscore.so")
+# ALS_LIB_TAG=<tag> loads libalscore_<tag>.so: a bring-up build (trace instrumentation, single class count) made with
+# ALS_BUILD_TAG=<tag> NVCC_EXTRA=... python -m semanticsegmentationactivelearning_b200.build -- never the shipped library
+_TAG = os.environ.get("ALS_LIB_TAG", "")
+LIB_PATH = os.path.join(PKG, "libalscore%s.so" % ("_" + _TAG if _TAG else ""))
 
 ALS_OK = 0
 ALS_ERR_INVALID = -1

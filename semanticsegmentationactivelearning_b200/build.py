@@ -9,7 +9,8 @@ import sys
 
 PKG = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(PKG, "csrc")
-LIB = os.path.join(PKG, "libalscore.so")
+_TAG = os.environ.get("ALS_BUILD_TAG", "")       # bring-up builds live beside the shipped library (see _lib.py)
+LIB = os.path.join(PKG, "libalscore%s.so" % ("_" + _TAG if _TAG else ""))
 SOURCES = ["score.cu", "head.cu", "select.cu", "synth.cu", "capi.cu"]
 HEADERS = ["common.cuh", "pixel_math.cuh", "tc05.cuh", "head.cuh", "score.cuh", "select.cuh", "synth.cuh", os.path.join("..", "..", "include", "alscore.h")]
 NVCC_FLAGS = [
@@ -35,7 +36,7 @@ def _stale(target: str, deps: list[str]) -> bool:
 def build(force: bool = False, verbose: bool = False) -> str:
     nvcc = _nvcc()
     hdrs = [os.path.normpath(os.path.join(CSRC, h)) for h in HEADERS] + [os.path.abspath(__file__)]
-    objdir = os.path.join(PKG, "build")
+    objdir = os.path.join(PKG, "build" + ("_" + _TAG if _TAG else ""))
     os.makedirs(objdir, exist_ok=True)
     jobs = []
     for src in SOURCES:

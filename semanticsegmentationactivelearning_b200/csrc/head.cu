@@ -48,9 +48,12 @@ namespace als {
 #ifdef ALS_HEAD_TRACE
 // Bring-up instrumentation (never built into the shipped library): SM-clock timestamps of CTA 0's first tiles.
 //   [tile][0..1] splitter start/end of the tile's row, [2..3] MMA issue start/end, [4] epilogue sees the accumulator,
-//   [5] epilogue released it, [6] epilogue done, [7] producer issued the row's copy
+//   [5] epilogue released it, [6] epilogue done, [7] producer issued the row's copy;  T > 1 (tile = accumulator =
+//   (tile, sample)): [0..1] is the CURRENT row, [8..9] the previous row's splitter start/end, [10] / [11] the moment
+//   the previous / current row's loader got its tensor-memory slot back from the MMAs
 constexpr int kTraceTiles = 1024;
-__device__ long long g_head_trace[kTraceTiles][8];
+constexpr int kTraceSlots = 16;  // T > 1: [12] [13] [14] = MMA warp past its wait for the previous row / current row / accumulator stage
+__device__ long long g_head_trace[kTraceTiles][kTraceSlots];
 #define ALS_TRACE(tile, slot)                                                         \
   do {                                                                                \
     if (blockIdx.x == 0 && (tile) < kTraceTiles) g_head_trace[(tile)][(slot)] = clock64(); \
@@ -295,6 +298,8 @@ __global__ void __launch_bounds__(Geom<C, EPB>::THREADS, 1) score_head_kernel(co
           for (int k = 0; k < un.rows; ++k)
             for (int t = 0; t < p.T; ++t) {
               issue_row(un.i0 + k - 1, t);
+              ALS_TRACE(ptile, 7);
+              ++ptile;
               issue_row(un.i0 + k, t);
             }
         }
@@ -367,9 +372,13 @@ __global__ void __launch_bounds__(Geom<C, EPB>::THREADS, 1) score_head_kernel(co
         const int n_acc = un.rows * p.T;
         for (int q = 0; q < n_acc; ++q, seq += 2) {
           const int rb_prev = seq & (kARing - 1), rb_cur = (seq + 1) & (kARing - 1);
+          if (leader) ALS_TRACE(tile, 15);
           mbar_wait(&full_a[rb_prev], (seq / kARing) & 1u);
+          if (leader) ALS_TRACE(tile, 12);
           mbar_wait(&full_a[rb_cur], ((seq + 1) / kARing) & 1u);
+          if (leader) ALS_TRACE(tile, 13);
           mbar_wait(&empty_acc[a], acc_ph ^ 1u);
+          if (leader) ALS_TRACE(tile, 14);
           tc05::fence_after_sync();
           if (leader) issue_tile(rb_prev, rb_cur, true);
           __syncwarp();
@@ -394,8 +403,10 @@ __global__ void __launch_bounds__(Geom<C, EPB>::THREADS, 1) score_head_kernel(co
       const Unit un = decode_unit(p, u);
       const int n_rows = MULTI ? 2 * un.rows * p.T : un.rows + 1;  // feature rows the producer sends for this unit
       for (int vr = 0; vr < n_rows; ++vr, ++rs) {
-        const int r = vr - 1;  // (trace only; single sample: row inside the unit)
-        if (r >= 0) ++stile;
+        const int r = MULTI ? 0 : vr - 1;  // (trace only; single sample: row inside the unit)
+        if (r >= 0 && !MULTI) ++stile;
+        if (MULTI) stile = (rs >> 1) + 1;
+        const int tr0 = (MULTI && !(rs & 1)) ? 8 : 0;  // (trace only) slot pair: previous row of a T > 1 accumulator -> 8, 9
         const int s_row = s;
         const uint32_t phs_row = phs;
         if (++s == kRawStages) { s = 0; phs ^= 1u; }
@@ -403,7 +414,7 @@ __global__ void __launch_bounds__(Geom<C, EPB>::THREADS, 1) score_head_kernel(co
         const int rb = rs & (kARing - 1);
         mbar_wait(&full_raw[s_row], phs_row);
         const RawMeta mt = meta[s_row];
-        if (r >= 0 && lt == 0) ALS_TRACE(stile - 1, 0);
+        if (r >= 0 && lt == 0) ALS_TRACE(stile - 1, tr0);
         // (a) transpose: 16-byte chunk q of the raw row -> plane (q & 3), pixel (q >> 2).  Both sides conflict free.
         asm volatile("bar.sync %0, %1;" ::"r"(1 + grp), "n"(kLoaderThreads) : "memory");  // previous row read out of `can_g`
         // chunk q = lt + 128 * it: plane lt & 3 (128 is a multiple of 4), pixel (lt >> 2) + 32 * it; 516 chunks in all
@@ -426,6 +437,7 @@ __global__ void __launch_bounds__(Geom<C, EPB>::THREADS, 1) score_head_kernel(co
         // (b) this thread's pixel (slot pixel m + 1) and its left neighbour (slot pixel m) -> tensor memory
         mbar_wait(&empty_a[rb], ((rs / kARing) & 1u) ^ 1u);  // the MMAs that read this slot completed
         tc05::fence_after_sync();
+        if (MULTI && lt == 0) ALS_TRACE(stile - 1, tr0 ? 10 : 11);
         const uint32_t t_row = t_lane + rb * kARowCols;
         float4 v[4];
 #pragma unroll
@@ -438,7 +450,7 @@ __global__ void __launch_bounds__(Geom<C, EPB>::THREADS, 1) score_head_kernel(co
         tc05::fence_before_sync();
         __syncwarp();
         if (lane == 0) mbar_arrive(&full_a[rb]);
-        if (r >= 0 && lt == 0) ALS_TRACE(stile - 1, 1);
+        if (r >= 0 && lt == 0) ALS_TRACE(stile - 1, tr0 + 1);
       }
     }
   } else if constexpr (!MULTI) {
@@ -522,6 +534,7 @@ __global__ void __launch_bounds__(Geom<C, EPB>::THREADS, 1) score_head_kernel(co
     ImageAcc acc;
     int a = 0;           // accumulator stage of the next (tile, sample) and its phase
     uint32_t ph = 0;
+    uint32_t tq = 0;     // (trace only) accumulators so far
     for (long long u = blockIdx.x; u < p.n_units; u += gridDim.x) {
       const Unit un = decode_unit(p, u);
       if (un.n != acc.img) {
@@ -543,6 +556,7 @@ __global__ void __launch_bounds__(Geom<C, EPB>::THREADS, 1) score_head_kernel(co
         for (int t = 0; t < p.T; ++t) {
           mbar_wait_relaxed(&full_acc[a], ph);
           tc05::fence_after_sync();
+          if (warp == 0 && lane == 0) ALS_TRACE(tq, 4);
           const float inv_t = __frcp_rn(static_cast<float>(t + 1));
           const uint32_t tacc = tbase + a * kAccStride;
 #pragma unroll
@@ -554,6 +568,7 @@ __global__ void __launch_bounds__(Geom<C, EPB>::THREADS, 1) score_head_kernel(co
               tc05::fence_before_sync();
               __syncwarp();
               if (lane == 0) mbar_arrive(&empty_acc[a]);
+              if (warp == 0 && lane == 0) ALS_TRACE(tq, 5);
             }
             float x[C];
 #pragma unroll
@@ -561,6 +576,8 @@ __global__ void __launch_bounds__(Geom<C, EPB>::THREADS, 1) score_head_kernel(co
             if (t == 0 && sp.label) lbl[b] = group_argmax<C, 1>(x, C, 0);  // pseudo_label of sample 0, as in score.cu
             welford_update<C, 1, true>(x, C, inv_t, nmu[b], m2s[b]);
           }
+          if (warp == 0 && lane == 0) ALS_TRACE(tq, 6);
+          ++tq;
           if (++a == kAccStages) { a = 0; ph ^= 1u; }
         }
         if (valid) {
@@ -654,7 +671,10 @@ size_t pack_head_weights(const float* kernel, int C, float* out) {
 
 // Monte-Carlo variant (T > 1): blocks per epilogue warp.  Two pixels of Welford state (2C + 2 registers) fit the
 // 112-register budget of the 576-thread CTA up to kHeadMaxClassesMC classes; above that the state would spill.
-constexpr int kEpbMulti = 2;
+#ifndef ALS_HEAD_EPB
+#define ALS_HEAD_EPB 2
+#endif
+constexpr int kEpbMulti = ALS_HEAD_EPB;
 
 template <int C>
 static const void* pick_head(int measure, int T, const char** name, int* block) {
@@ -677,8 +697,12 @@ static const void* pick_head(int measure, int T, const char** name, int* block) 
 }
 
 // One instantiation per class count 2..32 (the reference's datasets use 19, 6 and 19: datasets/*.py num_classes).
+#ifdef ALS_HEAD_ONLY_C  // bring-up builds: a single class count compiles in seconds
+#define ALS_HEAD_C_LIST(X) X(ALS_HEAD_ONLY_C)
+#else
 #define ALS_HEAD_C_LIST(X) X(2) X(3) X(4) X(5) X(6) X(7) X(8) X(9) X(10) X(11) X(12) X(13) X(14) X(15) X(16) X(17) X(18) \
   X(19) X(20) X(21) X(22) X(23) X(24) X(25) X(26) X(27) X(28) X(29) X(30) X(31) X(32)
+#endif
 
 template <int C>
 static bool geometry_agrees(const HeadGeom& g) {
@@ -716,7 +740,7 @@ HeadPlan plan_head(int C, int measure, int T, int num_sms) {
 #ifdef ALS_HEAD_TRACE
 extern "C" __attribute__((visibility("default"))) int als_debug_head_trace(long long* out, int tiles) {
   if (tiles > kTraceTiles) tiles = kTraceTiles;
-  return cudaMemcpyFromSymbol(out, g_head_trace, sizeof(long long) * 8 * tiles) == cudaSuccess ? tiles : -1;
+  return cudaMemcpyFromSymbol(out, g_head_trace, sizeof(long long) * kTraceSlots * tiles) == cudaSuccess ? tiles : -1;
 }
 #endif
 
