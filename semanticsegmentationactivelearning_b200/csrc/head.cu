@@ -20,10 +20,13 @@
 // operands are split x = hi + lo (hi = x rounded to tf32, lo = x - hi) and three products are accumulated in
 // fp32: hi*lo + lo*hi + hi*hi (the dropped lo*lo term and the tf32 rounding of the lo parts are ~2^-24 relative each).
 //
-// Data movement.  One 1-D bulk copy (TMA engine, UBLKCP) per feature row segment of 129 pixels (one halo
-// pixel on the left) into a raw ring in shared memory.  Four "loader" warps transpose it into 16-byte chunk
-// planes (so that a thread can read ITS pixel without bank conflicts: in NHWC a pixel is 64 B, half a bank
-// row), split every value into hi/lo in registers and write the A operands into TENSOR MEMORY with
+// Data movement.  The feature map is described to the TMA engine as a 4-D tensor [T*N][h][w][16 floats]; a feature
+// row segment of 129 pixels (one halo pixel on the left) arrives as four tiled copies with a box of 4 floats x 129
+// pixels each (cp.async.bulk.tensor, SASS UTMALDG): the engine itself lays the row out as 16-byte chunk PLANES in
+// shared memory (a thread can then read ITS pixel without bank conflicts: in NHWC a pixel is 64 B, half a bank row)
+// and zero-fills everything outside the image -- the row above the first, the pixel left of column 0, the columns
+// right of the last -- which is exactly TF's SAME padding.  "Loader" warps read their pixel and its left neighbour,
+// split every value into hi/lo in registers and write the A operands into TENSOR MEMORY with
 // tcgen05.st (lane = pixel, 16 columns = channels): own pixel and left neighbour, hi and lo = 64 columns per
 // feature row, a ring of three rows.  The MMAs take A from tensor memory and only the (small) weight
 // operand from shared memory -- with A in shared memory every one of the 24 MMAs of a tile re-read a 4 KB
@@ -36,6 +39,7 @@
 //   warp 20     MMA issuer (one elected lane), TMEM owner      warp 21  producer: bulk copies
 #include "head.cuh"
 
+#include <cuda.h>  // CUtensorMap (types only: the encoder is fetched through cudaGetDriverEntryPoint, no -lcuda)
 #include <math.h>
 #include <string.h>
 
@@ -71,19 +75,12 @@ constexpr int kARing = 4;                             // feature rows resident i
 constexpr int kARowCols = 64;                         // [own hi 16 | own lo 16 | left hi 16 | left lo 16]
 constexpr int kTmemCols = 512;
 constexpr int kSlotPx = kHeadTileQuads + 1;           // 129 pixels: one halo pixel on the left
-constexpr int kRawSlotBytes = 8320;                   // 129 * 64 rounded up to 128
-constexpr int kPlaneBytes = (kSlotPx + 1) * 16;       // 2080: stride between the 16-byte chunk planes of the transposed row
-constexpr int kCanBytes = 4 * kPlaneBytes;            // 8320: one transposed row
+constexpr int kPlaneCopyBytes = kSlotPx * 16;         // 2064: one TMA box = 4 channels of 129 pixels
+constexpr int kPlaneBytes = (kPlaneCopyBytes + 127) / 128 * 128;  // 2176: the planes of a row start 128-byte aligned
+constexpr int kRawSlotBytes = 4 * kPlaneBytes;        // 8704: one feature row segment as four chunk planes
 constexpr int kLoaderGroups = 2;                      // groups of four warps taking alternate feature rows
 constexpr int kLoaderThreads = 128;                   // per group
 constexpr int kHeaderBytes = 512;
-
-struct RawMeta {
-  int valid;  // quad columns of this strip that exist (<= 128)
-  int first;  // strip starts at image column 0: the halo pixel is padding
-  int zero;   // whole row is padding (row -1 of the image)
-  int pad_;
-};
 
 struct Unit {
   int n, i0, rows, j0, valid;
@@ -204,7 +201,8 @@ __device__ __forceinline__ void store_split(uint32_t taddr, const float4 (&v)[4]
 }
 
 template <int C, int MEASURE, int EPB>
-__global__ void __launch_bounds__(Geom<C, EPB>::THREADS, 1) score_head_kernel(const HeadParams p) {
+__global__ void __launch_bounds__(Geom<C, EPB>::THREADS, 1)
+score_head_kernel(const HeadParams p, const __grid_constant__ CUtensorMap feat_map) {
   using G = Geom<C, EPB>;
   constexpr bool MULTI = G::MULTI;  // T > 1: every tile is computed once per Monte-Carlo sample
   static_assert(MULTI == (MEASURE == kMulti), "T > 1 runs the kMulti instantiation (measure is a run-time field)");
@@ -225,10 +223,8 @@ __global__ void __launch_bounds__(Geom<C, EPB>::THREADS, 1) score_head_kernel(co
   uint64_t* empty_acc = full_acc + kAccStages;
   uint64_t* wbar = empty_acc + kAccStages;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + 256);
-  RawMeta* meta = reinterpret_cast<RawMeta*>(smem + 320);
   unsigned char* raw_base = smem + kHeaderBytes;
-  unsigned char* can = raw_base + kRawStages * kRawSlotBytes;
-  unsigned char* w_base = can + kLoaderGroups * kCanBytes;
+  unsigned char* w_base = raw_base + kRawStages * kRawSlotBytes;
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -236,7 +232,7 @@ __global__ void __launch_bounds__(Geom<C, EPB>::THREADS, 1) score_head_kernel(co
   if (threadIdx.x == 0) {
     for (int s = 0; s < kRawStages; ++s) {
       mbar_init(&full_raw[s], 1);
-      mbar_init(&empty_raw[s], kLoaderThreads / 32);
+      mbar_init(&empty_raw[s], kLoaderThreads / 32);  // the four warps (lane quarters) of the group that takes the row
     }
     for (int s = 0; s < kARing; ++s) {
       mbar_init(&full_a[s], kLoaderThreads / 32);
@@ -266,23 +262,17 @@ __global__ void __launch_bounds__(Geom<C, EPB>::THREADS, 1) score_head_kernel(co
       long long ptile = 0;
       for (long long u = blockIdx.x; u < p.n_units; u += gridDim.x) {
         const Unit un = decode_unit(p, u);
-        const int first = un.j0 == 0 ? 1 : 0;
-        // feature row `row` (-1 = the padding row above the image) of sample t -> next raw slot
+        // feature row `row` (-1 = the padding row above the image) of sample t -> next raw slot, as four chunk planes.
+        // Coordinates outside the tensor (row -1, pixel -1, pixels >= w) are zero-filled by the TMA engine and
+        // still count towards the transaction bytes.
         auto issue_row = [&](int row, int t) {
           mbar_wait_relaxed(&empty_raw[s], ph ^ 1u);
-          meta[s].valid = un.valid;
-          meta[s].first = first;
-          meta[s].zero = row < 0 ? 1 : 0;
-          if (row < 0) {
-            mbar_arrive_expect_tx(&full_raw[s], 0);
-          } else {
-            const float* src = p.features + t * p.sample_stride +
-                               ((static_cast<long long>(un.n) * p.h + row) * p.w + (un.j0 - (first ? 0 : 1))) * kHeadChannels;
-            const uint32_t bytes = static_cast<uint32_t>(un.valid + (first ? 0 : 1)) * 64u;
-            unsigned char* dst = raw_base + s * kRawSlotBytes + (first ? 64 : 0);
-            mbar_arrive_expect_tx(&full_raw[s], bytes);
-            bulk_g2s(dst, src, bytes, &full_raw[s], policy);
-          }
+          unsigned char* dst = raw_base + s * kRawSlotBytes;
+          const int img = t * p.n_images + un.n;
+          mbar_arrive_expect_tx(&full_raw[s], 4u * kPlaneCopyBytes);
+#pragma unroll
+          for (int c = 0; c < 4; ++c)
+            tc05::tma_load_4d(dst + c * kPlaneBytes, &feat_map, 4 * c, un.j0 - 1, row, img, &full_raw[s], policy);
           if (++s == kRawStages) { s = 0; ph ^= 1u; }
         };
         if constexpr (!MULTI) {
@@ -394,7 +384,6 @@ __global__ void __launch_bounds__(Geom<C, EPB>::THREADS, 1) score_head_kernel(co
     const int quarter = warp & 3;                        // TMEM lane quarter this warp may write
     const int m = quarter * 32 + lane;                   // A row = accumulator row = quad column inside the strip
     const uint32_t t_lane = tmem + (static_cast<uint32_t>(quarter * 32) << 16) + kACol0;
-    unsigned char* can_g = can + grp * kCanBytes;
     uint32_t rs = 0;      // feature rows seen so far: A-ring slot = rs & (kARing - 1)
     int s = 0;            // raw-ring slot of row rs and its phase
     uint32_t phs = 0;
@@ -413,39 +402,24 @@ __global__ void __launch_bounds__(Geom<C, EPB>::THREADS, 1) score_head_kernel(co
         if (kLoaderGroups > 1 && (rs & (kLoaderGroups - 1)) != static_cast<uint32_t>(grp)) continue;
         const int rb = rs & (kARing - 1);
         mbar_wait(&full_raw[s_row], phs_row);
-        const RawMeta mt = meta[s_row];
         if (r >= 0 && lt == 0) ALS_TRACE(stile - 1, tr0);
-        // (a) transpose: 16-byte chunk q of the raw row -> plane (q & 3), pixel (q >> 2).  Both sides conflict free.
-        asm volatile("bar.sync %0, %1;" ::"r"(1 + grp), "n"(kLoaderThreads) : "memory");  // previous row read out of `can_g`
-        // chunk q = lt + 128 * it: plane lt & 3 (128 is a multiple of 4), pixel (lt >> 2) + 32 * it; 516 chunks in all
-        const unsigned char* src = raw_base + s_row * kRawSlotBytes + lt * 16;
-        unsigned char* dst = can_g + (lt & 3) * kPlaneBytes + (lt >> 2) * 16;
-        const int px0 = lt >> 2;
-        const int lo_px = mt.zero ? (1 << 30) : (mt.first ? 1 : 0);  // pixels below lo_px / above valid are padding
-        float4 t[5];
+        // this thread's pixel (slot pixel m + 1) and its left neighbour (slot pixel m): 16-byte reads from the four
+        // chunk planes, consecutive lanes = consecutive 16-byte words
+        const unsigned char* rowp = raw_base + s_row * kRawSlotBytes + m * 16;
+        float4 own[4], left[4];
 #pragma unroll
-        for (int it = 0; it < 5; ++it) {
-          t[it] = make_float4(0.f, 0.f, 0.f, 0.f);
-          const int px = px0 + 32 * it;
-          if ((it < 4 || lt < 4) && px >= lo_px && px <= mt.valid) t[it] = *reinterpret_cast<const float4*>(src + it * 2048);
+        for (int c = 0; c < 4; ++c) {
+          own[c] = *reinterpret_cast<const float4*>(rowp + c * kPlaneBytes + 16);
+          left[c] = *reinterpret_cast<const float4*>(rowp + c * kPlaneBytes);
         }
-#pragma unroll
-        for (int it = 0; it < 5; ++it)
-          if (it < 4 || lt < 4) *reinterpret_cast<float4*>(dst + it * 512) = t[it];
-        asm volatile("bar.sync %0, %1;" ::"r"(1 + grp), "n"(kLoaderThreads) : "memory");
-        if (lane == 0) mbar_arrive(&empty_raw[s_row]);
-        // (b) this thread's pixel (slot pixel m + 1) and its left neighbour (slot pixel m) -> tensor memory
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&empty_raw[s_row]);  // release: the loads above are ordered before it
         mbar_wait(&empty_a[rb], ((rs / kARing) & 1u) ^ 1u);  // the MMAs that read this slot completed
         tc05::fence_after_sync();
         if (MULTI && lt == 0) ALS_TRACE(stile - 1, tr0 ? 10 : 11);
         const uint32_t t_row = t_lane + rb * kARowCols;
-        float4 v[4];
-#pragma unroll
-        for (int c = 0; c < 4; ++c) v[c] = *reinterpret_cast<const float4*>(can_g + c * kPlaneBytes + (m + 1) * 16);
-        store_split(t_row, v);
-#pragma unroll
-        for (int c = 0; c < 4; ++c) v[c] = *reinterpret_cast<const float4*>(can_g + c * kPlaneBytes + m * 16);
-        store_split(t_row + 32, v);
+        store_split(t_row, own);
+        store_split(t_row + 32, left);
         tc05::st_wait();
         tc05::fence_before_sync();
         __syncwarp();
@@ -669,20 +643,23 @@ size_t pack_head_weights(const float* kernel, int C, float* out) {
   return 2 * part;
 }
 
-// Monte-Carlo variant (T > 1): blocks per epilogue warp.  Two pixels of Welford state (2C + 2 registers) fit the
-// 112-register budget of the 576-thread CTA up to kHeadMaxClassesMC classes; above that the state would spill.
-#ifndef ALS_HEAD_EPB
-#define ALS_HEAD_EPB 2
+// Monte-Carlo variant (T > 1): blocks per epilogue warp.  One pixel per thread (16 epilogue warps, 832 threads,
+// 72 registers) holds the Welford state of up to 19 classes without spilling and gives the MUFU-bound update four
+// warps per scheduler; above that two pixels per thread (8 warps, 576 threads, 112 registers) up to
+// kHeadMaxClassesMC classes.  ALS_HEAD_EPB overrides the choice in bring-up builds.
+#ifdef ALS_HEAD_EPB
+__host__ __device__ constexpr int epb_multi(int) { return ALS_HEAD_EPB; }
+#else
+__host__ __device__ constexpr int epb_multi(int C) { return C <= 19 ? 1 : 2; }
 #endif
-constexpr int kEpbMulti = ALS_HEAD_EPB;
 
 template <int C>
 static const void* pick_head(int measure, int T, const char** name, int* block) {
   if (T > 1) {
     if constexpr (C <= kHeadMaxClassesMC) {
       *name = "score_head_kernel<multi>";
-      *block = Geom<C, kEpbMulti>::THREADS;
-      return (const void*)score_head_kernel<C, kMulti, kEpbMulti>;
+      *block = Geom<C, epb_multi(C)>::THREADS;
+      return (const void*)score_head_kernel<C, kMulti, epb_multi(C)>;
     } else {
       return nullptr;
     }
@@ -733,7 +710,7 @@ HeadPlan plan_head(int C, int measure, int T, int num_sms) {
     return plan;
   }
   plan.grid = num_sms;
-  plan.smem_bytes = kHeaderBytes + kRawStages * kRawSlotBytes + kLoaderGroups * kCanBytes + 2 * 4 * g.rows * 16;
+  plan.smem_bytes = kHeaderBytes + kRawStages * kRawSlotBytes + 2 * 4 * g.rows * 16;
   return plan;
 }
 
@@ -744,13 +721,42 @@ extern "C" __attribute__((visibility("default"))) int als_debug_head_trace(long 
 }
 #endif
 
+// The feature map as a 4-D tensor for the TMA engine: [T*N images][h rows][w pixels][16 floats], box = 4 floats x 129
+// pixels of one row (one 16-byte chunk plane of a row segment); out-of-range coordinates read as zero.
+static cudaError_t make_feature_map(const HeadParams& p, CUtensorMap* map) {
+  typedef CUresult (*EncodeFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                               const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                               CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+  static EncodeFn encode = [] {
+    void* fn = nullptr;
+    cudaDriverEntryPointQueryResult q = cudaDriverEntryPointSymbolNotFound;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &q) != cudaSuccess || q != cudaDriverEntryPointSuccess)
+      fn = nullptr;
+    return reinterpret_cast<EncodeFn>(fn);
+  }();
+  if (!encode) return cudaErrorNotSupported;
+  const cuuint64_t dims[4] = {static_cast<cuuint64_t>(kHeadChannels), static_cast<cuuint64_t>(p.w), static_cast<cuuint64_t>(p.h),
+                              static_cast<cuuint64_t>(p.T) * static_cast<cuuint64_t>(p.n_images)};
+  const cuuint64_t strides[3] = {kHeadChannels * sizeof(float), static_cast<cuuint64_t>(p.w) * kHeadChannels * sizeof(float),
+                                 static_cast<cuuint64_t>(p.h) * p.w * kHeadChannels * sizeof(float)};
+  const cuuint32_t box[4] = {4, static_cast<cuuint32_t>(kSlotPx), 1, 1};
+  const cuuint32_t estr[4] = {1, 1, 1, 1};
+  const CUresult r = encode(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, const_cast<float*>(p.features), dims, strides, box, estr,
+                            CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_NONE,
+                            CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  return r == CUDA_SUCCESS ? cudaSuccess : cudaErrorInvalidValue;
+}
+
 cudaError_t launch_head(const HeadPlan& plan, HeadParams p, cudaStream_t stream) {
   if (p.n_units <= 0) return cudaSuccess;
   p.sp.any_out = (p.sp.conf_map || p.sp.label || p.sp.mask) ? 1 : 0;
   cudaError_t err = cudaFuncSetAttribute(plan.func, cudaFuncAttributeMaxDynamicSharedMemorySize, plan.smem_bytes);
   if (err != cudaSuccess) return err;
   const long long grid = p.n_units < plan.grid ? p.n_units : plan.grid;
-  void* args[] = {&p};
+  alignas(64) CUtensorMap feat_map;
+  err = make_feature_map(p, &feat_map);
+  if (err != cudaSuccess) return err;
+  void* args[] = {&p, &feat_map};
   return cudaLaunchKernel(plan.func, dim3(static_cast<unsigned>(grid)), dim3(plan.block), args, plan.smem_bytes, stream);
 }
 

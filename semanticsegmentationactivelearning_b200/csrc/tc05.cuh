@@ -120,6 +120,17 @@ __device__ __forceinline__ void ld32(uint32_t taddr, float (&v)[32]) {
   for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]);
 }
 
+// ---- TMA tiled load of a 4-D box (coordinates innermost first), completion in bytes on `bar` -----------------
+// `tmap` points at a CUtensorMap in the kernel's parameter space (__grid_constant__); dst 128-byte aligned.
+__device__ __forceinline__ void tma_load_4d(void* dst, const void* tmap, int c0, int c1, int c2, int c3, uint64_t* bar,
+                                            uint64_t policy) {
+  asm volatile(
+      "cp.async.bulk.tensor.4d.shared::cluster.global.tile.mbarrier::complete_tx::bytes.L2::cache_hint"
+      " [%0], [%1, {%2, %3, %4, %5}], [%6], %7;"
+      ::"r"(smem_u32(dst)), "l"(tmap), "r"(c0), "r"(c1), "r"(c2), "r"(c3), "r"(smem_u32(bar)), "l"(policy)
+      : "memory");
+}
+
 // ---- registers -> TMEM: this thread's lane, 16 consecutive columns
 __device__ __forceinline__ void st16(uint32_t taddr, const uint32_t (&r)[16]) {
   asm volatile(
