@@ -28,15 +28,25 @@
 // right of the last -- which is exactly TF's SAME padding.  "Loader" warps read their pixel and its left neighbour,
 // split every value into hi/lo in registers and write the A operands into TENSOR MEMORY with
 // tcgen05.st (lane = pixel, 16 columns = channels): own pixel and left neighbour, hi and lo = 64 columns per
-// feature row, a ring of three rows.  The MMAs take A from tensor memory and only the (small) weight
+// feature row, a ring of four rows.  The MMAs take A from tensor memory and only the (small) weight
 // operand from shared memory -- with A in shared memory every one of the 24 MMAs of a tile re-read a 4 KB
 // A tile and the kernel was shared-memory bound at ~1000 clk / tile (profiles/r01_head_*).  A CTA walks
 // down a strip of 128 columns: each feature row is loaded once and used by two consecutive tiles.
 //
 // Roles (704 threads, 1 CTA / SM, persistent, static round-robin over units of R rows x 128 columns):
 //   warps 0-11  epilogue: 3 accumulator stages x 4 lane quarters
-//   warps 12-19 loaders: raw -> hi/lo A rows in TMEM (two groups of four warps, alternate rows)
-//   warp 20     MMA issuer (one elected lane), TMEM owner      warp 21  producer: bulk copies
+//   warps 12-19 loaders: chunk planes -> hi/lo A rows in TMEM (two groups of four warps, alternate rows)
+//   warp 20     MMA issuer (one elected lane), TMEM owner      warp 21  producer: TMA tile copies
+//
+// Monte-Carlo samples (T > 1, features [T,N,h,w,16]).  The Welford state of a pixel (running mean per class + summed
+// M2) has to stay in registers over the T samples, so the samples of ONE tile run back to back: accumulator q =
+// (tile, sample t), each with its own previous and current feature row (a row is therefore loaded and split twice,
+// the second time out of L2), and the epilogue is organised by BLOCK instead of by stage: 16 warps (lane quarter x
+// quad pixel) each take one pixel per thread of EVERY accumulator (8 warps x 2 pixels above 19 classes).  Measured
+// (profiles/head_trace.py, per-role clock64 timeline): the three roles -- loaders (2 rows per accumulator), the MMA
+// issuer (24 tcgen05.mma at ~25 clk of issue each + ~100 clk per mbarrier round trip) and the lock-stepped epilogue
+// warps (MUFU phase, then FMA phase) -- each need 1000-1300 clk per accumulator and couple through the 4-row A ring
+// and the 3 accumulator stages to ~1750 clk; knocking any single role out gains only 10-16 %.
 #include "head.cuh"
 
 #include <cuda.h>  // CUtensorMap (types only: the encoder is fetched through cudaGetDriverEntryPoint, no -lcuda)
@@ -170,14 +180,13 @@ __device__ __forceinline__ void ld_cols(uint32_t taddr, float (&v)[CNT]) {
 
 }  // namespace
 
-// one pixel (16 channels as 4 float4) -> hi and lo parts -> 2 x 16 tensor-memory columns of this thread's lane.
+// one pixel (16 channels as 4 float4) -> hi and lo parts (2 x 16 tensor-memory columns of this thread's lane).
 // The tensor core TRUNCATES its fp32 inputs to tf32 (probes/umma_probe.cu), so hi must be rounded here:
 // Veltkamp's split with 2^13 + 1 gives hi = x rounded to nearest on 11 significand bits and lo = x - hi exactly,
 // two packed FMA-pipe instructions per element pair each.  lo (|lo| <= 2^-11 |x|) is left to the hardware's
 // truncation: an error of at most 2^-21 |x|, the same order as the dropped lo*lo term.
-__device__ __forceinline__ void store_split(uint32_t taddr, const float4 (&v)[4]) {
+__device__ __forceinline__ void split_hi_lo(const float4 (&v)[4], uint32_t (&hi)[16], uint32_t (&lo)[16]) {
   const f32x2 k2 = pack2(8193.0f, 8193.0f), m1 = pack2(-1.0f, -1.0f);
-  uint32_t hi[16], lo[16];
 #pragma unroll
   for (int c = 0; c < 4; ++c) {
     const f32x2 x2[2] = {pack2(v[c].x, v[c].y), pack2(v[c].z, v[c].w)};
@@ -196,8 +205,6 @@ __device__ __forceinline__ void store_split(uint32_t taddr, const float4 (&v)[4]
       lo[4 * c + 2 * j + 1] = __float_as_uint(a1);
     }
   }
-  tc05::st16(taddr, hi);
-  tc05::st16(taddr + 16, lo);
 }
 
 template <int C, int MEASURE, int EPB>
@@ -254,6 +261,9 @@ score_head_kernel(const HeadParams p, const __grid_constant__ CUtensorMap feat_m
   if (warp == kProducerWarp) {
     // ===== producer =====
     if (lane == 0) {
+      // evict_first although the four plane copies of a row touch the same lines and T > 1 re-reads a row T samples
+      // later: measured 1.3 % faster than evict_normal on cfg1h and cfg2h (the re-reads still hit: the lines live
+      // long enough in the 126 MB L2)
       const uint64_t policy = l2_policy_evict_first();
       mbar_arrive_expect_tx(wbar, 2u * wpart_bytes);
       bulk_g2s(w_base, p.weights, 2u * wpart_bytes, wbar, policy);
@@ -360,7 +370,7 @@ score_head_kernel(const HeadParams p, const __grid_constant__ CUtensorMap feat_m
       } else {
         // T > 1: one accumulator per (tile, sample), each with its own pair of rows
         const int n_acc = un.rows * p.T;
-        for (int q = 0; q < n_acc; ++q, seq += 2) {
+        for (int q = 0; q < n_acc; ++q, seq += 2, ++tile) {
           const int rb_prev = seq & (kARing - 1), rb_cur = (seq + 1) & (kARing - 1);
           if (leader) ALS_TRACE(tile, 15);
           mbar_wait(&full_a[rb_prev], (seq / kARing) & 1u);
@@ -372,7 +382,6 @@ score_head_kernel(const HeadParams p, const __grid_constant__ CUtensorMap feat_m
           tc05::fence_after_sync();
           if (leader) issue_tile(rb_prev, rb_cur, true);
           __syncwarp();
-          ++tile;
           if (++a == kAccStages) { a = 0; acc_ph ^= 1u; }
         }
       }
@@ -414,12 +423,18 @@ score_head_kernel(const HeadParams p, const __grid_constant__ CUtensorMap feat_m
         }
         __syncwarp();
         if (lane == 0) mbar_arrive(&empty_raw[s_row]);  // release: the loads above are ordered before it
+        // split in registers while the tensor-memory slot may still be in use, then only the stores wait for it
+        uint32_t hi_o[16], lo_o[16], hi_l[16], lo_l[16];
+        split_hi_lo(own, hi_o, lo_o);
+        split_hi_lo(left, hi_l, lo_l);
         mbar_wait(&empty_a[rb], ((rs / kARing) & 1u) ^ 1u);  // the MMAs that read this slot completed
         tc05::fence_after_sync();
         if (MULTI && lt == 0) ALS_TRACE(stile - 1, tr0 ? 10 : 11);
         const uint32_t t_row = t_lane + rb * kARowCols;
-        store_split(t_row, own);
-        store_split(t_row + 32, left);
+        tc05::st16(t_row, hi_o);
+        tc05::st16(t_row + 16, lo_o);
+        tc05::st16(t_row + 32, hi_l);
+        tc05::st16(t_row + 48, lo_l);
         tc05::st_wait();
         tc05::fence_before_sync();
         __syncwarp();
