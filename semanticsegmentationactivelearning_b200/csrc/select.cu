@@ -8,6 +8,9 @@
 // Pools are small (<= a few 1e5 images), so one 1024-thread CTA does an MSB-first radix select
 // over the 96-bit virtual key (orderable(key):32 | biased id:64), 8 bits per pass, histogram in
 // shared memory; a second, multi-CTA kernel puts the k survivors in ascending order by ranking.
+// The select stops as soon as a digit bin holds exactly the elements still wanted (with distinct scores that is
+// after the four key passes at the latest: the eight id passes only run when the k-th boundary falls inside a
+// group of equal keys).
 #include "select.cuh"
 
 #include "common.cuh"
@@ -38,12 +41,14 @@ __global__ void __launch_bounds__(kSelThreads) select_threshold_kernel(const flo
   __shared__ unsigned long long s_id;
   __shared__ long long s_remaining;
   __shared__ unsigned int s_count;
+  __shared__ int s_done;
   const int tid = threadIdx.x;
   if (tid == 0) {
     s_ord = 0;
     s_id = 0;
     s_remaining = k;
     s_count = 0;
+    s_done = 0;
   }
   __syncthreads();
   if (k >= M) {
@@ -82,8 +87,19 @@ __global__ void __launch_bounds__(kSelThreads) select_threshold_kernel(const flo
         s_remaining = rem;
         if (pass < 4) s_ord |= d << (24 - 8 * pass);
         else s_id |= static_cast<unsigned long long>(d) << (56 - 8 * (pass - 4));
+        if (rem == static_cast<long long>(hist[d])) {
+          // every element with this prefix is wanted: the threshold is the largest virtual key with the prefix
+          if (pass < 4) {
+            s_ord |= (pass == 3) ? 0u : (0xffffffffu >> (8 * (pass + 1)));
+            s_id = ~0ull;
+          } else {
+            s_id |= (pass == 11) ? 0ull : (~0ull >> (8 * (pass - 3)));
+          }
+          s_done = 1;
+        }
       }
       __syncthreads();
+      if (s_done) break;
     }
   }
   __syncthreads();

@@ -256,6 +256,28 @@ def test_select_edge_cases(torch, scorer):
         assert np.array_equal(_np(ok), _np(keys)[order[:k]])
 
 
+def test_select_random_against_total_order(torch, scorer):
+    """The radix select stops early when a digit bin holds exactly the elements still wanted: exercise boundaries that
+    fall inside, at the end of and between groups of equal keys, with NaN / inf / signed zeros and negative ids."""
+    from oracle import reference_np as R
+    rng = np.random.default_rng(20191013)
+    for trial in range(60):
+        M = int(rng.choice([1, 2, 3, 17, 255, 256, 257, 1000, 2975, 18000]))
+        distinct = int(rng.choice([1, 2, 5, 50, 10 ** 6]))
+        vals = rng.standard_normal(distinct).astype(np.float32)
+        if trial % 3 == 0:
+            vals[: min(4, distinct)] = np.array([np.nan, np.inf, -0.0, 0.0], np.float32)[: min(4, distinct)]
+        keys = vals[rng.integers(0, distinct, M)]
+        ids = rng.permutation(4 * M)[:M].astype(np.int64) - (M if trial % 2 else 0)     # unique, some negative
+        for k in {0, 1, M // 2, max(M - 1, 0), M, M + 3, int(rng.integers(0, M + 1))}:
+            ok, oi = scorer.select_smallest(torch.from_numpy(keys).cuda(), torch.from_numpy(ids).cuda(), k)
+            # oracle: total order over (key with -0 == +0 and NaN last, id); confidence indexed by position
+            order = np.lexsort((ids, np.isnan(keys), np.where(np.isnan(keys), np.inf, keys + np.float32(0.0))))
+            want = order[: min(k, M)]
+            assert np.array_equal(_np(oi), ids[want]), (trial, M, distinct, k)
+            assert np.array_equal(_np(ok), keys[want], equal_nan=True), (trial, M, distinct, k)
+
+
 @pytest.mark.parametrize("measure,T", [("entropy", 1), ("margin", 1), ("confidence", 1), ("variance", 4)])
 def test_rank_confidence_end_to_end(torch, scorer, measure, T):
     """Whole closure: device and host (batched like sess.run, shuffled) against the oracle."""
