@@ -47,6 +47,11 @@
 // issuer (24 tcgen05.mma at ~25 clk of issue each + ~100 clk per mbarrier round trip) and the lock-stepped epilogue
 // warps (MUFU phase, then FMA phase) -- each need 1000-1300 clk per accumulator and couple through the 4-row A ring
 // and the 3 accumulator stages to ~1750 clk; knocking any single role out gains only 10-16 %.
+//
+// Issue rate of the tensor pipe (measured): a tcgen05.mma of this shape (M = 128, K = 8, N <= 80) occupies the pipe
+// for >= ~21-25 clk however narrow N is, and a second issuer warp does not change that (two issuers taking alternate
+// tiles: +3 % at C = 6, -4 % at C = 19) -- the 24 MMAs of a tile are a ~550-600 clk floor at every class count,
+// which is what bounds the kernel below C ~ 12 (770-850 clk per tile at C = 2...6).
 #include "head.cuh"
 
 #include <cuda.h>  // CUtensorMap (types only: the encoder is fetched through cudaGetDriverEntryPoint, no -lcuda)
