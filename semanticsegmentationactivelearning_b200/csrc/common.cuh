@@ -72,6 +72,28 @@ __device__ __forceinline__ void bulk_g2s(void* dst, const void* src, uint32_t by
       : "memory");
 }
 
+// ---- programmatic dependent launch ------------------------------------------------------------------------
+// Consecutive kernels of a pool pass are tiny next to their launch latency when batches are small (8 images =
+// ~50 us of HBM time).  A kernel launched with launch_pdl() may start while its predecessor in the stream is still
+// running; it must call pdl_wait() before it touches anything an earlier kernel wrote (then it sees all of it).
+// pdl_launch_dependents() lets the NEXT such kernel become resident early.  Both are no-ops without the attribute.
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+
+inline cudaError_t launch_pdl(const void* func, dim3 grid, dim3 block, void** args, size_t smem, cudaStream_t stream) {
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = grid;
+  cfg.blockDim = block;
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = stream;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  return cudaLaunchKernelExC(&cfg, func, args);
+}
+
 // ---- math -----------------------------------------------------------------------------
 __device__ __forceinline__ float ex2_approx(float x) {
   float y;

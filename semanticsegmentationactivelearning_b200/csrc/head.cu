@@ -262,6 +262,7 @@ score_head_kernel(const HeadParams p, const __grid_constant__ CUtensorMap feat_m
   __syncthreads();
   tc05::fence_after_sync();
   const uint32_t tmem = *tmem_slot;
+  pdl_launch_dependents();  // the finalize kernel behind this one may become resident now (it waits for our sums)
 
   if (warp == kProducerWarp) {
     // ===== producer =====

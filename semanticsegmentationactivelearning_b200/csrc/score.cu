@@ -163,6 +163,10 @@ __global__ void __launch_bounds__(kBlockThreads, Cfg<E, C, (MEASURE == kMulti)>:
     fence_mbar_init();
   }
   __syncthreads();
+  // everything above overlapped the tail of the previous kernel in the stream (programmatic dependent launch);
+  // from here on the logits, the accumulators and the tile counter are read
+  pdl_launch_dependents();
+  pdl_wait();
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -343,6 +347,8 @@ constexpr int kGenericThreads = 128;
 template <typename E>
 __global__ void __launch_bounds__(kGenericThreads) score_generic_kernel(const ScoreParams p) {
   extern __shared__ float mu_s[];  // [C][kGenericThreads] when T > 1
+  pdl_launch_dependents();
+  pdl_wait();
   const E* base = static_cast<const E*>(p.logits);
   const int C = p.C;
   long long acc_sum = 0, acc_img = -1;
@@ -443,6 +449,8 @@ __global__ void finalize_kernel(long long* __restrict__ acc, long long acc_strid
                                 unsigned long long* __restrict__ tile_counter, int n, double inv_scale_p,
                                 double* __restrict__ scores64, float* __restrict__ pool32,
                                 const long long* __restrict__ example_index, long long num_examples) {
+  pdl_launch_dependents();
+  pdl_wait();  // the scoring kernel's sums are complete and visible
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i == 0) *tile_counter = 0ull;  // ready for the next scoring launch on this stream
   if (i >= n) return;
@@ -466,9 +474,8 @@ cudaError_t launch_finalize(long long* acc, long long acc_stride, unsigned int* 
                             float* pool32, const long long* example_index, long long num_examples,
                             cudaStream_t stream) {
   if (n <= 0) return cudaSuccess;
-  finalize_kernel<<<(n + 255) / 256, 256, 0, stream>>>(acc, acc_stride, flags, tile_counter, n, inv_scale_p, scores64, pool32, example_index,
-                                                       num_examples);
-  return cudaGetLastError();
+  void* args[] = {&acc, &acc_stride, &flags, &tile_counter, &n, &inv_scale_p, &scores64, &pool32, &example_index, &num_examples};
+  return launch_pdl((const void*)finalize_kernel, dim3((n + 255) / 256), dim3(256), args, 0, stream);
 }
 
 // ---- dispatch ------------------------------------------------------------------------------------
@@ -568,7 +575,7 @@ cudaError_t launch_score(const LaunchPlan& plan, int dtype, ScoreParams p, cudaS
     p.stages = plan.stages;
     p.num_tiles = (p.total_pixels + plan.tile_pixels - 1) / plan.tile_pixels;
     void* args[] = {&p};
-    return cudaLaunchKernel(plan.func, dim3(plan.grid), dim3(plan.block), args, plan.smem_bytes, stream);
+    return launch_pdl(plan.func, dim3(plan.grid), dim3(plan.block), args, plan.smem_bytes, stream);
   }
   const void* f = dtype == 0 ? (const void*)score_generic_kernel<float> : (const void*)score_generic_kernel<__nv_bfloat16>;
   if (plan.smem_bytes > 48 * 1024) {
@@ -576,7 +583,7 @@ cudaError_t launch_score(const LaunchPlan& plan, int dtype, ScoreParams p, cudaS
     if (err != cudaSuccess) return err;
   }
   void* args[] = {&p};
-  return cudaLaunchKernel(f, dim3(plan.grid), dim3(plan.block), args, plan.smem_bytes, stream);
+  return launch_pdl(f, dim3(plan.grid), dim3(plan.block), args, plan.smem_bytes, stream);
 }
 
 }  // namespace als
