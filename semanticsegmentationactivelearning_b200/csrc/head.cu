@@ -477,11 +477,23 @@ score_head_kernel(const HeadParams p, const __grid_constant__ CUtensorMap feat_m
         if (quarter == 0 && lane == 0) ALS_TRACE(tile, 4);
         float conf[4];
         int lbl[4];
+        // the tensor-memory load of block b + 1 is in flight under the math of block b (+1.5 % at C = 19; above 28
+        // classes the second buffer would spill)
+        constexpr bool kPrefetch = (C <= 28);
+        float vn[kPrefetch ? 2 : 1][CB];
+        if constexpr (kPrefetch) ld_cols<CB>(tbase, vn[0]);
 #pragma unroll
         for (int b = 0; b < 4; ++b) {
           float v[CB];
-          ld_cols<CB>(tbase + b * CB, v);
-          tc05::ld_wait();
+          if constexpr (kPrefetch) {
+            tc05::ld_wait();
+#pragma unroll
+            for (int j = 0; j < CB; ++j) v[j] = vn[b & 1][j];
+            if (b < 3) ld_cols<CB>(tbase + (b + 1) * CB, vn[(b + 1) & 1]);
+          } else {
+            ld_cols<CB>(tbase + b * CB, v);
+            tc05::ld_wait();
+          }
           if (b == 3) {  // everything is in registers: hand the accumulator back to the MMA warp
             tc05::fence_before_sync();
             __syncwarp();
