@@ -452,7 +452,8 @@ def main():
         if head:
             desc = {"kernel": "score_head_kernel<%s> C=%d: tcgen05 split-TF32 UMMA 128xNx8 + TMEM epilogue" % (
                         measure if T == 1 else "multi", C),
-                    "grid": 148, "block": 704 if T == 1 else 576, "smem_bytes": None, "stages": 4, "tile_pixels": 512}
+                    "grid": 148, "block": (704 if C <= 20 else 576) if T == 1 else (832 if C <= 19 else 576),
+                    "smem_bytes": None, "stages": 4, "tile_pixels": 512}
         else:
             desc = sc.describe_launch(dtype, T, chunk, H, W, C, measure)
         line = {
