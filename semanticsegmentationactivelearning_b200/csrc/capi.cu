@@ -531,7 +531,8 @@ int check_features(als_ctx* ctx, const void* features, int64_t T, int64_t N, int
     return fail(ctx, ALS_ERR_UNSUPPORTED, "no fused-head kernel for C=%lld with T=%lld (use als_score on the logits)",
                 (long long)ctx->head_C, (long long)T);
   if (N < 0 || h < 1 || w < 1) return fail(ctx, ALS_ERR_INVALID, "bad feature shape [N=%lld,h=%lld,w=%lld,16]", (long long)N, (long long)h, (long long)w);
-  if (h > (1 << 20) || w > (1 << 20) || N > 0x7fffffff) return fail(ctx, ALS_ERR_INVALID, "feature map too large");
+  if (h > (1 << 20) || w > (1 << 20) || N > 0x7fffffff || T * N > 0x7fffffff)  // (sample, image) is one int32 TMA coordinate
+    return fail(ctx, ALS_ERR_INVALID, "feature map too large");
   if (want_label && ctx->head_C > 256) return fail(ctx, ALS_ERR_INVALID, "uint8 pseudo_label needs C <= 256");
   if (N > 0 && !features) return fail(ctx, ALS_ERR_INVALID, "features pointer is NULL");
   if (reinterpret_cast<uintptr_t>(features) % 16 != 0) return fail(ctx, ALS_ERR_INVALID, "features must be 16-byte aligned");
@@ -568,7 +569,6 @@ int score_features_device(als_ctx* ctx, const void* features, int64_t T, int64_t
   p.sp.label = label;
   p.sp.mask = mask;
   p.features = static_cast<const float*>(features);
-  p.sample_stride = N * h * w * als::kHeadChannels;
   p.T = static_cast<int>(T);
   p.weights = ctx->head_weights;
   p.h = static_cast<int>(h);

@@ -32,8 +32,7 @@ size_t pack_head_weights(const float* kernel, int C, float* out);
 
 struct HeadParams {
   ScoreParams sp;          // P = H*W of the OUTPUT (2h x 2w); acc / flags / outputs / fx_scale as in score.cu
-  const float* features;   // [T][N][h][w][16] fp32, 16-byte aligned
-  long long sample_stride; // elements between Monte-Carlo samples = N*h*w*16
+  const float* features;   // [T][N][h][w][16] fp32, 16-byte aligned (read through a TMA tensor map: sample t, image n = tensor row t*N + n)
   int T;                   // samples (1 = the reference's single forward pass)
   const float* weights;    // packed B image (pack_head_weights), device
   int h, w;                // input (feature) height / width; output is 2h x 2w
