@@ -21,11 +21,15 @@
 // fp32: hi*lo + lo*hi + hi*hi (the dropped lo*lo term and the tf32 rounding of the lo parts are ~2^-24 relative each).
 //
 // Data movement.  The feature map is described to the TMA engine as a 4-D tensor [T*N][h][w][16 floats]; a feature
-// row segment of 129 pixels (one halo pixel on the left) arrives as four tiled copies with a box of 4 floats x 129
-// pixels each (cp.async.bulk.tensor, SASS UTMALDG): the engine itself lays the row out as 16-byte chunk PLANES in
-// shared memory (a thread can then read ITS pixel without bank conflicts: in NHWC a pixel is 64 B, half a bank row)
-// and zero-fills everything outside the image -- the row above the first, the pixel left of column 0, the columns
-// right of the last -- which is exactly TF's SAME padding.  "Loader" warps read their pixel and its left neighbour,
+// row segment of 129 pixels (one halo pixel on the left) arrives as ONE tiled copy with a box of 16 floats x 129
+// pixels and the 64-byte swizzle (cp.async.bulk.tensor, SASS UTMALDG): the engine stores the 16-byte chunk c of pixel
+// px at chunk position c ^ ((px >> 1) & 3) inside the pixel's 64 bytes, so a thread can read ITS pixel with four
+// 16-byte loads without bank conflicts (unswizzled, a pixel is half a bank row and eight lanes collide four ways),
+// and it zero-fills everything outside the image -- the row above the first, the pixel left of column 0, the columns
+// right of the last -- which is exactly TF's SAME padding.  (First version: 1-D bulk copies + a transpose through
+// shared memory with two bar.sync per row.  Second: four unswizzled boxes of 4 floats x 129 pixels = chunk planes;
+// 516 sixteen-byte box rows per feature row kept the TMA engine busy for ~12 % of the kernel.)  "Loader" warps read
+// their pixel and its left neighbour,
 // split every value into hi/lo in registers and write the A operands into TENSOR MEMORY with
 // tcgen05.st (lane = pixel, 16 columns = channels): own pixel and left neighbour, hi and lo = 64 columns per
 // feature row, a ring of four rows.  The MMAs take A from tensor memory and only the (small) weight
@@ -90,9 +94,10 @@ constexpr int kARing = 4;                             // feature rows resident i
 constexpr int kARowCols = 64;                         // [own hi 16 | own lo 16 | left hi 16 | left lo 16]
 constexpr int kTmemCols = 512;
 constexpr int kSlotPx = kHeadTileQuads + 1;           // 129 pixels: one halo pixel on the left
-constexpr int kPlaneCopyBytes = kSlotPx * 16;         // 2064: one TMA box = 4 channels of 129 pixels
-constexpr int kPlaneBytes = (kPlaneCopyBytes + 127) / 128 * 128;  // 2176: the planes of a row start 128-byte aligned
-constexpr int kRawSlotBytes = 4 * kPlaneBytes;        // 8704: one feature row segment as four chunk planes
+constexpr int kRowCopyBytes = kSlotPx * 64;           // 8256: one TMA box = 129 pixels x 16 channels
+constexpr int kRawSlotBytes = 8704;                   // ... in a slot that keeps the 512-byte phase of the 64-byte swizzle
+constexpr int kRawAlign = 512;
+static_assert(kRawSlotBytes % kRawAlign == 0 && kRawSlotBytes >= kRowCopyBytes, "raw ring slots");
 constexpr int kLoaderGroups = 2;                      // groups of four warps taking alternate feature rows
 constexpr int kLoaderThreads = 128;                   // per group
 constexpr int kHeaderBytes = 512;
@@ -235,7 +240,8 @@ score_head_kernel(const HeadParams p, const __grid_constant__ CUtensorMap feat_m
   uint64_t* empty_acc = full_acc + kAccStages;
   uint64_t* wbar = empty_acc + kAccStages;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + 256);
-  unsigned char* raw_base = smem + kHeaderBytes;
+  // the raw ring starts on a 512-byte boundary of the shared-memory WINDOW (the swizzle is a function of the address)
+  unsigned char* raw_base = smem + kHeaderBytes + ((kRawAlign - ((smem_u32(smem) + kHeaderBytes) & (kRawAlign - 1))) & (kRawAlign - 1));
   unsigned char* w_base = raw_base + kRawStages * kRawSlotBytes;
 
   const int warp = threadIdx.x >> 5;
@@ -285,10 +291,8 @@ score_head_kernel(const HeadParams p, const __grid_constant__ CUtensorMap feat_m
           mbar_wait_relaxed(&empty_raw[s], ph ^ 1u);
           unsigned char* dst = raw_base + s * kRawSlotBytes;
           const int img = t * p.n_images + un.n;
-          mbar_arrive_expect_tx(&full_raw[s], 4u * kPlaneCopyBytes);
-#pragma unroll
-          for (int c = 0; c < 4; ++c)
-            tc05::tma_load_4d(dst + c * kPlaneBytes, &feat_map, 4 * c, un.j0 - 1, row, img, &full_raw[s], policy);
+          mbar_arrive_expect_tx(&full_raw[s], kRowCopyBytes);
+          tc05::tma_load_4d(dst, &feat_map, 0, un.j0 - 1, row, img, &full_raw[s], policy);
           if (++s == kRawStages) { s = 0; ph ^= 1u; }
         };
         if constexpr (!MULTI) {
@@ -420,12 +424,17 @@ score_head_kernel(const HeadParams p, const __grid_constant__ CUtensorMap feat_m
         if (r >= 0 && lt == 0) ALS_TRACE(stile - 1, tr0);
         // this thread's pixel (slot pixel m + 1) and its left neighbour (slot pixel m): 16-byte reads from the four
         // chunk planes, consecutive lanes = consecutive 16-byte words
-        const unsigned char* rowp = raw_base + s_row * kRawSlotBytes + m * 16;
+        // 64-byte swizzle: 16-byte chunk c of slot pixel px sits at chunk position c ^ ((px >> 1) & 3) of its 64 bytes,
+        // so the eight lanes of a quarter-warp (consecutive pixels, same c) hit eight different 4-bank groups
+        const unsigned char* rowp = raw_base + s_row * kRawSlotBytes;
+        const unsigned char* own_p = rowp + (m + 1) * 64;
+        const unsigned char* left_p = rowp + m * 64;
+        const int own_x = ((m + 1) >> 1) & 3, left_x = (m >> 1) & 3;
         float4 own[4], left[4];
 #pragma unroll
         for (int c = 0; c < 4; ++c) {
-          own[c] = *reinterpret_cast<const float4*>(rowp + c * kPlaneBytes + 16);
-          left[c] = *reinterpret_cast<const float4*>(rowp + c * kPlaneBytes);
+          own[c] = *reinterpret_cast<const float4*>(own_p + ((c ^ own_x) << 4));
+          left[c] = *reinterpret_cast<const float4*>(left_p + ((c ^ left_x) << 4));
         }
         __syncwarp();
         if (lane == 0) mbar_arrive(&empty_raw[s_row]);  // release: the loads above are ordered before it
@@ -743,7 +752,7 @@ HeadPlan plan_head(int C, int measure, int T, int num_sms) {
     return plan;
   }
   plan.grid = num_sms;
-  plan.smem_bytes = kHeaderBytes + kRawStages * kRawSlotBytes + 2 * 4 * g.rows * 16;
+  plan.smem_bytes = kHeaderBytes + kRawAlign + kRawStages * kRawSlotBytes + 2 * 4 * g.rows * 16;
   return plan;
 }
 
@@ -772,10 +781,10 @@ static cudaError_t make_feature_map(const HeadParams& p, CUtensorMap* map) {
                               static_cast<cuuint64_t>(p.T) * static_cast<cuuint64_t>(p.n_images)};
   const cuuint64_t strides[3] = {kHeadChannels * sizeof(float), static_cast<cuuint64_t>(p.w) * kHeadChannels * sizeof(float),
                                  static_cast<cuuint64_t>(p.h) * p.w * kHeadChannels * sizeof(float)};
-  const cuuint32_t box[4] = {4, static_cast<cuuint32_t>(kSlotPx), 1, 1};
+  const cuuint32_t box[4] = {static_cast<cuuint32_t>(kHeadChannels), static_cast<cuuint32_t>(kSlotPx), 1, 1};
   const cuuint32_t estr[4] = {1, 1, 1, 1};
   const CUresult r = encode(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, const_cast<float*>(p.features), dims, strides, box, estr,
-                            CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_NONE,
+                            CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_64B, CU_TENSOR_MAP_L2_PROMOTION_NONE,
                             CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   return r == CUDA_SUCCESS ? cudaSuccess : cudaErrorInvalidValue;
 }
