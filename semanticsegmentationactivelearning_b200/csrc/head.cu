@@ -37,10 +37,10 @@
 // A tile and the kernel was shared-memory bound at ~1000 clk / tile (profiles/r01_head_*).  A CTA walks
 // down a strip of 128 columns: each feature row is loaded once and used by two consecutive tiles.
 //
-// Roles (704 threads, 1 CTA / SM, persistent, static round-robin over units of R rows x 128 columns):
-//   warps 0-11  epilogue: 3 accumulator stages x 4 lane quarters
-//   warps 12-19 loaders: chunk planes -> hi/lo A rows in TMEM (two groups of four warps, alternate rows)
-//   warp 20     MMA issuer (one elected lane), TMEM owner      warp 21  producer: TMA tile copies
+// Roles (576 threads, 1 CTA / SM, persistent, static round-robin over units of R rows x 128 columns):
+//   warps 0-11  epilogue: 3 accumulator stages x 4 lane quarters (2 stages above 20 classes)
+//   warps 12-15 loaders: swizzled rows -> hi/lo A rows in TMEM (T > 1: two groups of four warps, alternate rows)
+//   warp 16     MMA issuer (one elected lane), TMEM owner      warp 17  producer: TMA tile copies
 //
 // Monte-Carlo samples (T > 1, features [T,N,h,w,16]).  The Welford state of a pixel (running mean per class + summed
 // M2) has to stay in registers over the T samples, so the samples of ONE tile run back to back: accumulator q =
@@ -98,7 +98,7 @@ constexpr int kRowCopyBytes = kSlotPx * 64;           // 8256: one TMA box = 129
 constexpr int kRawSlotBytes = 8704;                   // ... in a slot that keeps the 512-byte phase of the 64-byte swizzle
 constexpr int kRawAlign = 512;
 static_assert(kRawSlotBytes % kRawAlign == 0 && kRawSlotBytes >= kRowCopyBytes, "raw ring slots");
-constexpr int kLoaderGroups = 2;                      // groups of four warps taking alternate feature rows
+constexpr int kMaxLoaderGroups = 2;                   // groups of four warps taking alternate feature rows
 constexpr int kLoaderThreads = 128;                   // per group
 constexpr int kHeaderBytes = 512;
 
@@ -146,9 +146,15 @@ struct Geom {
   static constexpr int EPI_WARPS = MULTI ? 16 / EPB : 4 * ACC_STAGES;
   static constexpr int ACC_ARRIVALS = MULTI ? EPI_WARPS : 4;  // epilogue warps that release one accumulator stage
   static constexpr int FIRST_LOADER_WARP = EPI_WARPS;  // warps below: epilogue, lane quarter = warp & 3 (stage or block group = warp >> 2)
-  static constexpr int MMA_WARP = FIRST_LOADER_WARP + 4 * kLoaderGroups;
+  // Loader groups of four warps taking alternate feature rows.  One sample needs one row per tile: a single group keeps
+  // up (the TMA engine lays the row out, the group only splits and stores it) and the eight warps saved leave the
+  // epilogue 96 registers -- measured +2.5 % at C = 19, +8 % at C = 6 against two groups.  T > 1 needs two rows per
+  // accumulator and keeps two groups.
+  static constexpr int LOADER_GROUPS = MULTI ? 2 : 1;
+  static_assert(LOADER_GROUPS <= kMaxLoaderGroups, "loader groups");
+  static constexpr int MMA_WARP = FIRST_LOADER_WARP + 4 * LOADER_GROUPS;
   static constexpr int PRODUCER_WARP = MMA_WARP + 1;
-  static constexpr int THREADS = 32 * (PRODUCER_WARP + 1);   // 704 (3 stages) or 576 (2 stages, or T > 1 with EPB = 2)
+  static constexpr int THREADS = 32 * (PRODUCER_WARP + 1);   // 576 (3 stages) or 448 (2 stages); T > 1: 832 (EPB = 1) or 576 (EPB = 2)
 };
 
 // TMEM -> registers, CNT consecutive columns (CNT multiple of 4, <= 32)
@@ -418,7 +424,7 @@ score_head_kernel(const HeadParams p, const __grid_constant__ CUtensorMap feat_m
         const int s_row = s;
         const uint32_t phs_row = phs;
         if (++s == kRawStages) { s = 0; phs ^= 1u; }
-        if (kLoaderGroups > 1 && (rs & (kLoaderGroups - 1)) != static_cast<uint32_t>(grp)) continue;
+        if (G::LOADER_GROUPS > 1 && (rs & (G::LOADER_GROUPS - 1)) != static_cast<uint32_t>(grp)) continue;
         const int rb = rs & (kARing - 1);
         mbar_wait(&full_raw[s_row], phs_row);
         if (r >= 0 && lt == 0) ALS_TRACE(stile - 1, tr0);
@@ -486,37 +492,32 @@ score_head_kernel(const HeadParams p, const __grid_constant__ CUtensorMap feat_m
         if (quarter == 0 && lane == 0) ALS_TRACE(tile, 4);
         float conf[4];
         int lbl[4];
-        // the tensor-memory load of block b + 1 is in flight under the math of block b (+1.5 % at C = 19; above 28
-        // classes the second buffer would spill)
-        constexpr bool kPrefetch = (C <= 28);
-        float vn[kPrefetch ? 2 : 1][CB];
-        if constexpr (kPrefetch) ld_cols<CB>(tbase, vn[0]);
+        // two blocks at a time: the two pixels' dependent chains (max -> ex2 -> sums -> lg2 / rcp) interleave in the
+        // instruction stream (+1.2 % at C = 19 on top of the single loader group that pays for the registers)
 #pragma unroll
-        for (int b = 0; b < 4; ++b) {
-          float v[CB];
-          if constexpr (kPrefetch) {
-            tc05::ld_wait();
+        for (int bp = 0; bp < 2; ++bp) {
+          float v0[CB], v1[CB];
+          ld_cols<CB>(tbase + (2 * bp) * CB, v0);
+          ld_cols<CB>(tbase + (2 * bp + 1) * CB, v1);
+          tc05::ld_wait();
+          float x[2][C];
 #pragma unroll
-            for (int j = 0; j < CB; ++j) v[j] = vn[b & 1][j];
-            if (b < 3) ld_cols<CB>(tbase + (b + 1) * CB, vn[(b + 1) & 1]);
-          } else {
-            ld_cols<CB>(tbase + b * CB, v);
-            tc05::ld_wait();
-          }
-          if (b == 3) {  // everything is in registers: hand the accumulator back to the MMA warp
+          for (int j = 0; j < C; ++j) { x[0][j] = v0[j]; x[1][j] = v1[j]; }
+          if (bp == 1) {  // everything is in registers: hand the accumulator back to the MMA warp
             tc05::fence_before_sync();
             __syncwarp();
             if (lane == 0) mbar_arrive(&empty_acc[a]);
             if (quarter == 0 && lane == 0) ALS_TRACE(tile, 5);
           }
-          float x[C];
 #pragma unroll
-          for (int j = 0; j < C; ++j) x[j] = v[j];
-          lbl[b] = sp.label ? group_argmax<C, 1>(x, C, 0) : 0;
-          conf[b] = conf_single<C, 1, true, MEASURE>(x, C, sp);
+          for (int q = 0; q < 2; ++q) lbl[2 * bp + q] = sp.label ? group_argmax<C, 1>(x[q], C, 0) : 0;
+          conf[2 * bp] = conf_single<C, 1, true, MEASURE>(x[0], C, sp);
+          conf[2 * bp + 1] = conf_single<C, 1, true, MEASURE>(x[1], C, sp);
           if constexpr (MEASURE == kEntropy) {
-            if (__any_sync(0xffffffffu, !(conf[b] == conf[b])))  // rare: -inf / NaN logits
-              conf[b] = conf_single<C, 1, true, MEASURE, true>(x, C, sp);
+            if (__any_sync(0xffffffffu, !(conf[2 * bp] == conf[2 * bp]) || !(conf[2 * bp + 1] == conf[2 * bp + 1]))) {
+              conf[2 * bp] = conf_single<C, 1, true, MEASURE, true>(x[0], C, sp);       // rare: -inf / NaN logits
+              conf[2 * bp + 1] = conf_single<C, 1, true, MEASURE, true>(x[1], C, sp);
+            }
           }
         }
         if (quarter == 0 && lane == 0) ALS_TRACE(tile, 6);
