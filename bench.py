@@ -452,7 +452,7 @@ def main():
         if head:
             desc = {"kernel": "score_head_kernel<%s> C=%d: tcgen05 split-TF32 UMMA 128xNx8 + TMEM epilogue" % (
                         measure if T == 1 else "multi", C),
-                    "grid": 148, "block": (704 if C <= 20 else 576) if T == 1 else (832 if C <= 19 else 576),
+                    "grid": 148, "block": (576 if C <= 20 else 448) if T == 1 else (832 if C <= 19 else 576),
                     "smem_bytes": None, "stages": 4, "tile_pixels": 512}
         else:
             desc = sc.describe_launch(dtype, T, chunk, H, W, C, measure)
@@ -481,8 +481,8 @@ def main():
             # the fused kernel is not HBM bound: say what limits it and how busy the tensor pipe is
             from semanticsegmentationactivelearning_b200.acquisition import head_mma_flops_per_pixel
             fl = head_mma_flops_per_pixel(C)
-            line["roofline"]["limiter"] = ("SM issue slots + MUFU (19 ex2 + lg2 + rcp per pixel); ncu: XU pipe 66 %, tensor pipe 59 %, "
-                                           "issue 57 %, DRAM 23 % (profiles/r01_ncu_full_cfg1h.txt)")
+            line["roofline"]["limiter"] = ("SM issue slots + MUFU (19 ex2 + lg2 + rcp per pixel); ncu: XU pipe 71 %, tensor pipe 63 %, "
+                                           "issue 54 %, DRAM 25 % (profiles/r01_ncu_full_cfg1h.txt)")
             line["roofline"]["tensor"] = {"kind": "tf32, 3-product split (hi*lo + lo*hi + hi*hi)", "flops_per_pixel": fl,
                                           "achieved_tflops": fl * T * chunks[0][2] * P / (avg_ms * 1e-3) / 1e12,
                                           "nominal_peak_tflops": 1100.0}
