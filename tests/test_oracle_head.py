@@ -96,3 +96,34 @@ def test_packed_operands_reproduce_the_transposed_convolution(Cn):
     # padding columns of every block carry zero weights
     for b in range(4):
         assert not np.any(D[:, :, b * CB + Cn:(b + 1) * CB])
+
+
+def test_head_support_matrix_is_decided_on_the_host():
+    """als_head_supported (class count x measure x Monte-Carlo samples) needs no GPU: 2..32 classes for one sample,
+    2..24 with T > 1 (the Welford state of a pixel pair has to fit the register file), variance only with T >= 2."""
+    from semanticsegmentationactivelearning_b200 import _lib
+    lib = _lib.load()
+    ent, mar, con, var = 0, 1, 2, 3
+    for c in range(2, 33):
+        assert all(lib.als_head_supported(c, m, 1) == 1 for m in (ent, mar, con)), c
+        assert lib.als_head_supported(c, var, 1) == 0
+        for t in (2, 8, 16):
+            want = 1 if c <= 24 else 0
+            assert all(lib.als_head_supported(c, m, t) == want for m in (ent, mar, con, var)), (c, t)
+    for c in (0, 1, 33, 66):
+        assert lib.als_head_supported(c, ent, 1) == 0
+    assert lib.als_head_supported(19, ent, 0) == 0 and lib.als_head_supported(19, 7, 1) == 0
+
+
+def test_torch_restatement_runs_the_layer_per_monte_carlo_sample():
+    """reference_torch.final_head on [T,N,h,w,16] = the layer applied to each sample (bench CPU baseline of cfg2h)."""
+    import torch
+    from oracle import reference_torch as RT
+    rng = np.random.default_rng(5)
+    feat = rng.standard_normal((3, 2, 4, 5, 16)).astype(np.float32)
+    kern = (0.4 * rng.standard_normal((3, 3, 7, 16))).astype(np.float32)
+    got = RT.final_head(torch.from_numpy(feat), torch.from_numpy(kern)).numpy()
+    want = np.stack([R.final_head(feat[t], kern) for t in range(3)])
+    np.testing.assert_allclose(got, want, rtol=0, atol=2e-5)
+    s_t = RT.score_pool(torch.from_numpy(want), "variance").numpy()
+    np.testing.assert_allclose(s_t, R.score_pool(want, "variance"), rtol=1e-6)
