@@ -452,7 +452,7 @@ def main():
         if head:
             desc = {"kernel": "score_head_kernel<%s> C=%d: tcgen05 split-TF32 UMMA 128xNx8 + TMEM epilogue" % (
                         measure if T == 1 else "multi", C),
-                    "grid": 148, "block": (576 if C <= 20 else 448) if T == 1 else (832 if C <= 19 else 576),
+                    "grid": 148, "block": (576 if C <= 20 else 448) if T == 1 else 448,
                     "smem_bytes": None, "stages": 4, "tile_pixels": 512}
         else:
             desc = sc.describe_launch(dtype, T, chunk, H, W, C, measure)

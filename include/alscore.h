@@ -150,7 +150,7 @@ ALS_API int als_head_geometry(int64_t C, int32_t* geom14, int32_t* rows);
 ALS_API int als_head_pack_weights(const float* kernel, int64_t C, float* out, int64_t out_floats);
 
 /* 1 if a fused-head kernel exists for (C, measure, T samples), else 0: 2 <= C <= 32 for T == 1,
- * 2 <= C <= 24 for T >= 2 (the per-class Welford state of a pixel pair has to fit the register file). */
+ * 2 <= C <= 24 for T >= 2 (the per-class Welford state of two pixels has to fit a thread's registers). */
 ALS_API int als_head_supported(int64_t C, int measure, int64_t T);
 
 /*

@@ -45,8 +45,8 @@
 // Monte-Carlo samples (T > 1, features [T,N,h,w,16]).  The Welford state of a pixel (running mean per class + summed
 // M2) has to stay in registers over the T samples, so the samples of ONE tile run back to back: accumulator q =
 // (tile, sample t), each with its own previous and current feature row (a row is therefore loaded and split twice,
-// the second time out of L2), and the epilogue is organised by BLOCK instead of by stage: 16 warps (lane quarter x
-// quad pixel) each take one pixel per thread of EVERY accumulator (8 warps x 2 pixels above 19 classes).  Measured
+// the second time out of L2), and the epilogue is organised by BLOCK instead of by stage: 8 warps (lane quarter x
+// quad-pixel pair) each take two pixels per thread of EVERY accumulator, their two update chains interleaved.  Measured
 // (profiles/head_trace.py, per-role clock64 timeline): the three roles -- loaders (2 rows per accumulator), the MMA
 // issuer (24 tcgen05.mma at ~25 clk of issue each + ~100 clk per mbarrier round trip) and the lock-stepped epilogue
 // warps (MUFU phase, then FMA phase) -- each need 1000-1300 clk per accumulator and couple through the 4-row A ring
@@ -146,15 +146,15 @@ struct Geom {
   static constexpr int EPI_WARPS = MULTI ? 16 / EPB : 4 * ACC_STAGES;
   static constexpr int ACC_ARRIVALS = MULTI ? EPI_WARPS : 4;  // epilogue warps that release one accumulator stage
   static constexpr int FIRST_LOADER_WARP = EPI_WARPS;  // warps below: epilogue, lane quarter = warp & 3 (stage or block group = warp >> 2)
-  // Loader groups of four warps taking alternate feature rows.  One sample needs one row per tile: a single group keeps
-  // up (the TMA engine lays the row out, the group only splits and stores it) and the eight warps saved leave the
-  // epilogue 96 registers -- measured +2.5 % at C = 19, +8 % at C = 6 against two groups.  T > 1 needs two rows per
-  // accumulator and keeps two groups.
-  static constexpr int LOADER_GROUPS = MULTI ? 2 : 1;
+  // Loader groups of four warps taking alternate feature rows.  A single group keeps up now that the TMA engine lays
+  // the rows out (the group only splits and stores them), and the warps saved buy registers for the epilogue:
+  // T = 1: 576 threads / 96 registers, +2.5 % at C = 19 and +8 % at C = 6 against two groups;  T > 1 (two rows per
+  // accumulator): 448 threads / 128 registers with two pixels per epilogue thread, +8 % against 832 threads.
+  static constexpr int LOADER_GROUPS = 1;
   static_assert(LOADER_GROUPS <= kMaxLoaderGroups, "loader groups");
   static constexpr int MMA_WARP = FIRST_LOADER_WARP + 4 * LOADER_GROUPS;
   static constexpr int PRODUCER_WARP = MMA_WARP + 1;
-  static constexpr int THREADS = 32 * (PRODUCER_WARP + 1);   // 576 (3 stages) or 448 (2 stages); T > 1: 832 (EPB = 1) or 576 (EPB = 2)
+  static constexpr int THREADS = 32 * (PRODUCER_WARP + 1);   // 576 (3 stages) or 448 (2 stages); T > 1: 448 (EPB = 2)
 };
 
 // TMEM -> registers, CNT consecutive columns (CNT multiple of 4, <= 32)
@@ -576,6 +576,26 @@ score_head_kernel(const HeadParams p, const __grid_constant__ CUtensorMap feat_m
           if (warp == 0 && lane == 0) ALS_TRACE(tq, 4);
           const float inv_t = __frcp_rn(static_cast<float>(t + 1));
           const uint32_t tacc = tbase + a * kAccStride;
+          if constexpr (EPB == 2) {
+            // both pixels' accumulator blocks first, then their updates back to back: two independent dependent chains
+            float v0[CB], v1[CB];
+            ld_cols<CB>(tacc, v0);
+            ld_cols<CB>(tacc + CB, v1);
+            tc05::ld_wait();
+            tc05::fence_before_sync();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&empty_acc[a]);
+            if (warp == 0 && lane == 0) ALS_TRACE(tq, 5);
+            float x[2][C];
+#pragma unroll
+            for (int j = 0; j < C; ++j) { x[0][j] = v0[j]; x[1][j] = v1[j]; }
+            if (t == 0 && sp.label) {
+              lbl[0] = group_argmax<C, 1>(x[0], C, 0);
+              lbl[1] = group_argmax<C, 1>(x[1], C, 0);
+            }
+            welford_update<C, 1, true>(x[0], C, inv_t, nmu[0], m2s[0]);
+            welford_update<C, 1, true>(x[1], C, inv_t, nmu[1], m2s[1]);
+          } else {
 #pragma unroll
           for (int b = 0; b < EPB; ++b) {
             float v[CB];
@@ -592,6 +612,7 @@ score_head_kernel(const HeadParams p, const __grid_constant__ CUtensorMap feat_m
             for (int j = 0; j < C; ++j) x[j] = v[j];
             if (t == 0 && sp.label) lbl[b] = group_argmax<C, 1>(x, C, 0);  // pseudo_label of sample 0, as in score.cu
             welford_update<C, 1, true>(x, C, inv_t, nmu[b], m2s[b]);
+          }
           }
           if (warp == 0 && lane == 0) ALS_TRACE(tq, 6);
           ++tq;
@@ -686,14 +707,14 @@ size_t pack_head_weights(const float* kernel, int C, float* out) {
   return 2 * part;
 }
 
-// Monte-Carlo variant (T > 1): blocks per epilogue warp.  One pixel per thread (16 epilogue warps, 832 threads,
-// 72 registers) holds the Welford state of up to 19 classes without spilling and gives the MUFU-bound update four
-// warps per scheduler; above that two pixels per thread (8 warps, 576 threads, 112 registers) up to
-// kHeadMaxClassesMC classes.  ALS_HEAD_EPB overrides the choice in bring-up builds.
+// Monte-Carlo variant (T > 1): blocks per epilogue warp.  Two pixels per thread (8 epilogue warps; with the single
+// loader group 448 threads and up to 128 registers) hold the Welford state of up to kHeadMaxClassesMC classes and let
+// the two pixels' update chains interleave; one pixel per thread (16 warps) measured 8 % slower.  ALS_HEAD_EPB
+// overrides the choice in bring-up builds.
 #ifdef ALS_HEAD_EPB
 __host__ __device__ constexpr int epb_multi(int) { return ALS_HEAD_EPB; }
 #else
-__host__ __device__ constexpr int epb_multi(int C) { return C <= 19 ? 1 : 2; }
+__host__ __device__ constexpr int epb_multi(int) { return 2; }
 #endif
 
 template <int C>
