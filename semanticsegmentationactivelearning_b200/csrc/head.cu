@@ -129,10 +129,10 @@ __host__ __device__ constexpr int cmax(int a, int b) { return a > b ? a : b; }
 // stage and all four blocks of its lane quarter.  2 or 1: Monte-Carlo samples (T > 1) -- the per-class Welford state
 // of four pixels does not fit one thread, so the blocks are split over 16 / EPB warps that all work on the SAME
 // accumulator and keep the state of their EPB pixels in registers across the T samples of a tile.
-template <int C, int EPB = 4>
+template <int C, int EPB = 4, bool MULTI_ = false>
 struct Geom {
   static_assert(EPB == 4 || EPB == 2 || EPB == 1, "blocks per epilogue warp");
-  static constexpr bool MULTI = EPB < 4;
+  static constexpr bool MULTI = MULTI_;
   static constexpr int CB = cround(C, 4);
   static constexpr int N1 = cround(2 * CB, 16), N2 = cround(2 * CB, 16), N3 = cround(CB, 16);
   static constexpr int N0 = cround(cmax(4 * CB, cmax(N1, cmax(CB + N2, CB + N3))), 16);  // also initialises every column
@@ -224,9 +224,9 @@ __device__ __forceinline__ void split_hi_lo(const float4 (&v)[4], uint32_t (&hi)
 }
 
 template <int C, int MEASURE, int EPB>
-__global__ void __launch_bounds__(Geom<C, EPB>::THREADS, 1)
+__global__ void __launch_bounds__(Geom<C, EPB, (MEASURE == kMulti)>::THREADS, 1)
 score_head_kernel(const HeadParams p, const __grid_constant__ CUtensorMap feat_map) {
-  using G = Geom<C, EPB>;
+  using G = Geom<C, EPB, (MEASURE == kMulti)>;
   constexpr bool MULTI = G::MULTI;  // T > 1: every tile is computed once per Monte-Carlo sample
   static_assert(MULTI == (MEASURE == kMulti), "T > 1 runs the kMulti instantiation (measure is a run-time field)");
   constexpr int CB = G::CB;
@@ -576,25 +576,31 @@ score_head_kernel(const HeadParams p, const __grid_constant__ CUtensorMap feat_m
           if (warp == 0 && lane == 0) ALS_TRACE(tq, 4);
           const float inv_t = __frcp_rn(static_cast<float>(t + 1));
           const uint32_t tacc = tbase + a * kAccStride;
-          if constexpr (EPB == 2) {
-            // both pixels' accumulator blocks first, then their updates back to back: two independent dependent chains
-            float v0[CB], v1[CB];
-            ld_cols<CB>(tacc, v0);
-            ld_cols<CB>(tacc + CB, v1);
-            tc05::ld_wait();
-            tc05::fence_before_sync();
-            __syncwarp();
-            if (lane == 0) mbar_arrive(&empty_acc[a]);
-            if (warp == 0 && lane == 0) ALS_TRACE(tq, 5);
-            float x[2][C];
+          if constexpr (EPB % 2 == 0) {
+            // a pair of pixels at a time: both accumulator blocks first, then the two updates back to back (two
+            // independent dependent chains in the instruction stream)
 #pragma unroll
-            for (int j = 0; j < C; ++j) { x[0][j] = v0[j]; x[1][j] = v1[j]; }
-            if (t == 0 && sp.label) {
-              lbl[0] = group_argmax<C, 1>(x[0], C, 0);
-              lbl[1] = group_argmax<C, 1>(x[1], C, 0);
+            for (int bp = 0; bp < EPB / 2; ++bp) {
+              float v0[CB], v1[CB];
+              ld_cols<CB>(tacc + (2 * bp) * CB, v0);
+              ld_cols<CB>(tacc + (2 * bp + 1) * CB, v1);
+              tc05::ld_wait();
+              if (bp == EPB / 2 - 1) {  // this warp's share is in registers
+                tc05::fence_before_sync();
+                __syncwarp();
+                if (lane == 0) mbar_arrive(&empty_acc[a]);
+                if (warp == 0 && lane == 0) ALS_TRACE(tq, 5);
+              }
+              float x[2][C];
+#pragma unroll
+              for (int j = 0; j < C; ++j) { x[0][j] = v0[j]; x[1][j] = v1[j]; }
+              if (t == 0 && sp.label) {
+                lbl[2 * bp] = group_argmax<C, 1>(x[0], C, 0);
+                lbl[2 * bp + 1] = group_argmax<C, 1>(x[1], C, 0);
+              }
+              welford_update<C, 1, true>(x[0], C, inv_t, nmu[2 * bp], m2s[2 * bp]);
+              welford_update<C, 1, true>(x[1], C, inv_t, nmu[2 * bp + 1], m2s[2 * bp + 1]);
             }
-            welford_update<C, 1, true>(x[0], C, inv_t, nmu[0], m2s[0]);
-            welford_update<C, 1, true>(x[1], C, inv_t, nmu[1], m2s[1]);
           } else {
 #pragma unroll
           for (int b = 0; b < EPB; ++b) {
@@ -709,7 +715,8 @@ size_t pack_head_weights(const float* kernel, int C, float* out) {
 
 // Monte-Carlo variant (T > 1): blocks per epilogue warp.  Two pixels per thread (8 epilogue warps; with the single
 // loader group 448 threads and up to 128 registers) hold the Welford state of up to kHeadMaxClassesMC classes and let
-// the two pixels' update chains interleave; one pixel per thread (16 warps) measured 8 % slower.  ALS_HEAD_EPB
+// the two pixels' update chains interleave; one pixel per thread (16 warps) measured 8 % slower, four pixels per
+// thread (4 warps, 166 registers) 12 % slower.  ALS_HEAD_EPB
 // overrides the choice in bring-up builds.
 #ifdef ALS_HEAD_EPB
 __host__ __device__ constexpr int epb_multi(int) { return ALS_HEAD_EPB; }
@@ -722,7 +729,7 @@ static const void* pick_head(int measure, int T, const char** name, int* block) 
   if (T > 1) {
     if constexpr (C <= kHeadMaxClassesMC) {
       *name = "score_head_kernel<multi>";
-      *block = Geom<C, epb_multi(C)>::THREADS;
+      *block = Geom<C, epb_multi(C), true>::THREADS;
       return (const void*)score_head_kernel<C, kMulti, epb_multi(C)>;
     } else {
       return nullptr;
