@@ -4,8 +4,8 @@
     python bench.py [--gpus N] [--steps K] [--warmup W] [--workload cfg2] [--impl reference]
 
 One "step" = one pass of the hot path over the whole synthetic pool of the workload:
-als_pool_begin -> als_pool_score_batch per chunk -> als_pool_select (+ NCCL all-gather of the
-per-GPU candidates when N > 1).  Default workload = BASELINE.json configs[1] (ENet MC-dropout T=8
+als_pool_begin -> als_pool_score_batch per chunk -> als_pool_select; when N > 1 the selection is
+als_pool_select_global: per-GPU candidates on the device, ONE ncclAllGather, merge on the device.  Default workload = BASELINE.json configs[1] (ENet MC-dropout T=8
 variance, 2975 images @512x1024, C=19, fp32).  Multi-GPU is weak scaling: every rank scores its
 own 2975-image shard of an N x 2975 pool; the only exchange is the candidate/score all-gather.
 
@@ -234,6 +234,36 @@ def run_reference(args):
     print(json.dumps(line), flush=True)
 
 
+def pin_to_gpu_cpus(local_rank: int) -> dict:
+    """Bind this rank to the CPUs next to its GPU's PCIe root (pinned staging buffers are then allocated on that
+    node).  Best effort: containers often expose one NUMA node and the same CPU list for every GPU."""
+    info = {"numa_node": None, "cpus": None, "pinned": False}
+    try:
+        out = subprocess.run(["nvidia-smi", "--query-gpu=pci.bus_id", "--format=csv,noheader", "-i", str(local_rank)],
+                             capture_output=True, text=True, timeout=10).stdout.strip()       # 00000000:1B:00.0
+        dom, rest = out.split(":", 1)
+        bus = dom[-4:] + ":" + rest                                                                # 0000:1B:00.0
+        dev = "/sys/bus/pci/devices/" + str(bus).lower()
+        with open(dev + "/numa_node") as f:
+            info["numa_node"] = int(f.read().strip())
+        with open(dev + "/local_cpulist") as f:
+            cpus = set()
+            for part in f.read().strip().split(","):
+                if "-" in part:
+                    a, b = part.split("-"); cpus.update(range(int(a), int(b) + 1))
+                elif part:
+                    cpus.add(int(part))
+        allowed = os.sched_getaffinity(0)
+        use = sorted(cpus & allowed)
+        info["cpus"] = "%d local of %d allowed" % (len(use), len(allowed))
+        if use and len(use) < len(allowed):
+            os.sched_setaffinity(0, use)
+            info["pinned"] = True
+    except Exception as e:   # pragma: no cover
+        info["error"] = str(e)[:80]
+    return info
+
+
 # ------------------------------------------------------------------------------------------------
 def main():
     args = parse_args()
@@ -243,7 +273,7 @@ def main():
 
     import torch
     import torch.distributed as dist
-    from semanticsegmentationactivelearning_b200 import Scorer, rank_confidence_sharded
+    from semanticsegmentationactivelearning_b200 import Scorer, comm_init_torch
 
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -251,6 +281,7 @@ def main():
     if not torch.cuda.is_available():
         raise SystemExit("bench.py needs a GPU (the pool-scoring path has no CPU fallback)")
     torch.cuda.set_device(local_rank)
+    affinity = pin_to_gpu_cpus(local_rank)
     dev = torch.device("cuda", local_rank)
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
@@ -269,6 +300,8 @@ def main():
     id0 = rank * N                                    # this rank's global example ids: [id0, id0 + N)
 
     sc = Scorer(local_rank)
+    if world > 1:
+        comm_init_torch(sc)                           # the library's own NCCL communicator (csrc/comm.cu)
     head = bool(w.get("head"))
     n_chunk_bufs = resident // chunk
     if head:
@@ -308,8 +341,7 @@ def main():
             buf = sc.synth_logits(T, id0 + n0, nb, H, W, C, dtype=dtype, seed=SEED, squeeze_t=False)
         chunks.append((buf, n0, nb))
         n0 += nb
-    unl_local = np.arange(N, dtype=np.int64)          # every pool image is unlabelled
-    unl_global = np.arange(world * N, dtype=np.int64)
+    unl_global = np.arange(world * N, dtype=np.int64)   # every pool image is unlabelled
 
     ev_pairs = []
     maps = bool(w.get("maps"))
@@ -317,9 +349,10 @@ def main():
     map_outs = {}
 
     def step(record: bool):
-        sc.pool_begin(N)
+        # every rank keeps the full-size confidence vector and scores the ids it owns: [id0, id0 + N)
+        sc.pool_begin(world * N)
         for buf, first, nb in chunks:
-            idx = np.arange(first, first + nb, dtype=np.int64)
+            idx = np.arange(id0 + first, id0 + first + nb, dtype=np.int64)
             if record:
                 e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
                 e0.record()
@@ -332,13 +365,10 @@ def main():
             if record:
                 e1.record()
                 ev_pairs.append((e0, e1, nb))
-        if world == 1:
-            ids, conf = sc.pool_select(unl_local, K_SELECT)
-        else:
-            scores = sc.pool_scores(N)
-            ids, conf = rank_confidence_sharded(scores, id0 + unl_local, unl_global, K_SELECT, scorer=sc,
-                                                    max_unlabelled_per_rank=N)
-        return ids, conf
+        if maps:
+            return None, None                  # the training-path call site has no selection (:229-275)
+        # :705-715; N > 1: local candidates -> one ncclAllGather -> merge, all on the device, one D2H
+        return sc.pool_select_global(unl_global, K_SELECT, (id0, id0 + N), N)
 
     def barrier():
         if world > 1:
@@ -368,6 +398,27 @@ def main():
         ms_total = float(t.item())
     ms_step = ms_total / args.steps
     value = world * N * P / (ms_step * 1e-3) / 1e9
+
+    # ---- outside the timed region: the merged ids against the oracle's selection on the same score vector ----
+    ids_check = None
+    if not maps:
+        full_scores = sc.pool_scores(world * N)       # after the exchange every rank holds the whole vector
+        if rank == 0:
+            from oracle import reference_np as R
+            want_ids, want_u = R.select_lowest(full_scores, unl_global, K_SELECT)     # np.argpartition, :705-714
+            # the synthetic pool aliases `resident` distinct images, so scores repeat and the k-th boundary falls inside
+            # a group of EQUAL scores, where np.argpartition's choice is arbitrary: compare the selected score multiset
+            # and require every id strictly below the k-th score on both sides
+            kth = np.sort(full_scores[want_ids])[-1] if len(want_ids) else np.float32(0)
+            below = lambda sel: sorted(int(i) for i in sel if full_scores[i] < kth)
+            same = (sorted(full_scores[ids].tolist()) == sorted(full_scores[want_ids].tolist()) and below(ids) == below(want_ids))
+            ids_check = {"ids_match_oracle": bool(same),
+                         "unlabelled_confidence_match": bool(np.array_equal(conf, want_u)),
+                         "scores_finite": bool(np.all(np.isfinite(full_scores))),
+                         "distinct_scores": int(len(np.unique(full_scores))),
+                         "how": "oracle/reference_np.select_lowest (np.argpartition, :705-714) on the GPU path's own float32 "
+                                "score vector of the last timed pass; equal ids below the k-th score, equal score multiset "
+                                "(ties at the k-th score excused: the synthetic pool aliases its resident images)"}
 
     # dominant kernel: score_tiles_kernel, one launch per chunk (the 2 us finalize launch rides along)
     full = [(a.elapsed_time(b), nb) for a, b, nb in ev_pairs if nb == chunk] or [(a.elapsed_time(b), nb) for a, b, nb in ev_pairs]
@@ -401,36 +452,48 @@ def main():
              "outputs": "scores only",
              "note": "score+finalize launched back to back on one resident chunk, outside the timed region"}
 
-    # ---- e2e: the public API with HOST (pinned) logits, H2D inside the timed region ----------------
-    e2e = None
-    if not args.no_e2e and not maps:
-        from semanticsegmentationactivelearning_b200 import rank_confidence
-        per_img = T * (P // 4) * 64 if head else T * P * C * es
+    # ---- e2e: the public API with HOST (pinned) inputs, H2D inside the timed region ----------------
+    from semanticsegmentationactivelearning_b200 import rank_confidence
+
+    def measure_e2e(kind: str):
+        """kind: "native" = what the workload feeds (f32/bf16 logits, or features for the *h workloads);
+        "bf16" = the same logits rounded to bfloat16; "features" = the `Final` layer's input + fused head."""
+        use_head = head or kind == "features"
+        e_es = 2 if (kind == "bf16" or args.dtype == "bf16") else 4
+        per_img = T * (P // 4) * 64 if use_head else T * P * C * e_es
         bsz = max(1, min(8, int((2 << 30) // per_img)))              # images per sess.run-like batch (<= 8, :689)
-        n_e2e = max(bsz, min(N, int((8 << 30) // per_img) // bsz * bsz))   # ~8 GB of logits per step
-        tdt = torch.float32 if args.dtype == "f32" else torch.bfloat16
-        if head:
-            host = torch.empty((bsz, H // 2, W // 2, 16) if T == 1 else (T, bsz, H // 2, W // 2, 16), dtype=tdt).pin_memory()
-            host.copy_(bufs[0][:bsz] if T == 1 else bufs[0][:, :bsz])
+        n_e2e = max(bsz, min(N, int((8 << 30) // per_img) // bsz * bsz))   # ~8 GB of input per step
+        if use_head:
+            if head:
+                src = bufs[0][:bsz] if T == 1 else bufs[0][:, :bsz]
+                kern = head_kernel
+            else:
+                g2 = torch.Generator(device=dev); g2.manual_seed(SEED + 17 + rank)
+                src = torch.randn(((bsz, H // 2, W // 2, 16) if T == 1 else (T, bsz, H // 2, W // 2, 16)), generator=g2,
+                                  device=dev, dtype=torch.float32)
+                kern = (0.4 * np.random.default_rng(SEED).standard_normal((3, 3, C, 16))).astype(np.float32)
+            host = torch.empty(tuple(src.shape), dtype=torch.float32).pin_memory()
+            host.copy_(src)
         else:
+            kern = None
+            tdt = torch.bfloat16 if e_es == 2 else torch.float32
             host = torch.empty((T, bsz, H, W, C), dtype=tdt).pin_memory()
-            host.copy_(bufs[0][:, :bsz])
+            host.copy_(bufs[0][:, :bsz].to(tdt))
         torch.cuda.synchronize()
+        one = host if (T > 1 or use_head) else host[0]
 
         def e2e_step():
-            one = host if (T > 1 or head) else host[0]
             batches = ((one, np.arange(i, i + bsz, dtype=np.int64)) for i in range(0, n_e2e, bsz))
             return rank_confidence(batches, np.arange(n_e2e, dtype=np.int64), K_SELECT, measure, num_examples=n_e2e,
-                                   scorer=sc, head_kernel=head_kernel if head else None)
+                                   scorer=sc, head_kernel=kern)
 
         e2e_step()
         barrier()
-        t0 = time.perf_counter()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()
         k_e2e = max(2, min(args.steps, 5))
         for _ in range(k_e2e):
-            ids_e, conf_e = e2e_step()
+            e2e_step()
         e1.record()
         barrier()
         ms_e = e0.elapsed_time(e1) / k_e2e
@@ -438,11 +501,27 @@ def main():
             t = torch.tensor([ms_e], device=dev)
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
             ms_e = float(t.item())
-        e2e = {"value": world * n_e2e * P / (ms_e * 1e-3) / 1e9, "unit": "Gpix/s",
-               "h2d_bytes_per_step": int(n_e2e * per_img + n_e2e * 8 + n_e2e * 8),
-               "d2h_bytes_per_step": int(min(K_SELECT, n_e2e) * 8 + n_e2e * 4),
-               "pool_images_per_step": n_e2e, "batch_images": bsz, "ms_per_step": ms_e,
-               "note": "rank_confidence() fed pinned host batches like sess.run (:697-700); PCIe-bound"}
+        h2d = int(n_e2e * per_img + n_e2e * 8 + n_e2e * 8)
+        return {"value": world * n_e2e * P / (ms_e * 1e-3) / 1e9, "unit": "Gpix/s",
+                "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": int(min(K_SELECT, n_e2e) * 8 + n_e2e * 4),
+                "pool_images_per_step": n_e2e, "batch_images": bsz, "ms_per_step": ms_e,
+                "h2d_GBps_per_gpu": h2d / (ms_e * 1e-3) / 1e9,
+                "input": ("Final-layer features f32 [%sB,%d,%d,16] + fused head" % ("T," if T > 1 else "", H // 2, W // 2)) if use_head
+                         else ("%s logits [%sB,%d,%d,%d]" % ("bf16" if e_es == 2 else "f32", "T," if T > 1 else "", H, W, C)),
+                "note": "rank_confidence() fed pinned host batches like sess.run (:697-700); PCIe-bound"}
+
+    e2e = None
+    e2e_alt = None
+    if not args.no_e2e and not maps:
+        e2e = measure_e2e("native")
+        # the two byte-reducing inputs the library accepts for the same pool pass (same metric, fewer bytes over PCIe)
+        e2e_alt = {}
+        if not head and args.dtype == "f32":
+            e2e_alt["bf16_logits"] = measure_e2e("bf16")
+        if not head and Scorer.head_supported(C, measure, T):
+            e2e_alt["fused_head_features"] = measure_e2e("features")
+            if world == 1:
+                sc.pool_begin(N)
 
     if rank == 0:
         cpu = None
@@ -450,10 +529,7 @@ def main():
             rate, cores, sample = cpu_reference_rate(w, args.cpu_seconds, dtype)
             cpu = {"value": rate / 1e9, "unit": "Gpix/s", "cores": cores, "kind": "port", "sample": sample}
         if head:
-            desc = {"kernel": "score_head_kernel<%s> C=%d: tcgen05 split-TF32 UMMA 128xNx8 + TMEM epilogue" % (
-                        measure if T == 1 else "multi", C),
-                    "grid": 148, "block": (576 if C <= 20 else 448) if T == 1 else 448,
-                    "smem_bytes": None, "stages": 4, "tile_pixels": 512}
+            desc = sc.describe_head_launch(T, measure)
         else:
             desc = sc.describe_launch(dtype, T, chunk, H, W, C, measure)
         line = {
@@ -467,7 +543,7 @@ def main():
                        "l2": "inputs larger than L2 (resident set %.1f GB, aliased over the pool)" % (
                            resident * T * ((P // 4) * 64 if head else P * C * es) / 1e9),
                        "kernel": desc},
-            "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches * world),
+            "clocks": clocks, "e2e": e2e, "e2e_alt": e2e_alt, "gpu_launches": int(launches * world),
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                          "traffic": load_traffic(args.workload, args.dtype) if not args.pool else None,
                          "traffic_source": "profiles/ncu_traffic.json (dram__bytes_read+write of one ncu --set full launch)",
@@ -475,7 +551,8 @@ def main():
                          "bytes_per_launch": bytes_launch, "avg_launch_ms": avg_ms, "launches_timed": len(full),
                          "kernel_share_of_step": kernel_share, "kernel_burst": burst},
             "cpu_baseline": cpu,
-            "selected_ids_head": [int(i) for i in ids[:5]],
+            "selected_ids_head": [int(i) for i in ids[:5]] if ids is not None else None,
+            "ids_check": ids_check, "cpu_affinity": affinity,
         }
         if head:
             # the fused kernel is not HBM bound: say what limits it and how busy the tensor pipe is

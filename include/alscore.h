@@ -16,8 +16,13 @@
  *     staged to the GPU (never scored on the CPU -- there is no CPU fallback).
  *   - every function returns ALS_OK (0) or a negative als_status; the message is
  *     available from als_last_error().  Outputs are never partially filled on error.
- *   - calls are synchronous with respect to the host unless a function says otherwise;
- *     `stream` is a cudaStream_t (NULL = the context's own stream).
+ *   - calls are synchronous with respect to the host unless a function says otherwise.
+ *   - a `stream` argument is a cudaStream_t: NULL is the legacy default stream (what frameworks call "the default
+ *     stream"), ALS_STREAM_CTX is the context's stream.  Entries without a `stream` argument (the als_pool_*,
+ *     als_mc_* and *_host families) run on the context's stream, see als_ctx_set_stream.
+ *   - a context owns ONE set of per-image accumulators.  Calls on different streams are allowed: a call whose stream
+ *     differs from the previous call's first waits (on the device) for that call's kernels, so the scratch is never
+ *     shared by two launches in flight.  One context per host thread.
  */
 #ifndef ALSCORE_H_
 #define ALSCORE_H_
@@ -29,7 +34,10 @@
 extern "C" {
 #endif
 
-#define ALS_VERSION 100 /* 0.1.0 */
+#define ALS_VERSION 110 /* 0.1.1 */
+
+/* `stream` argument meaning "the context's stream" (NULL is the legacy default stream). */
+#define ALS_STREAM_CTX ((void*)(intptr_t)-1)
 
 #if defined(__GNUC__)
 #define ALS_API __attribute__((visibility("default")))
@@ -71,9 +79,10 @@ ALS_API int als_device_count(void);
 ALS_API int als_ctx_create(int device, als_ctx** out);
 ALS_API int als_ctx_destroy(als_ctx* ctx);
 
-/* Make all of the context's work run on the caller's cudaStream_t (e.g. the framework's current
- * stream, so scoring is ordered after the kernels that produced the logits).  The context does
- * not take ownership.  NULL is the legacy default stream. */
+/* Make the context's stream the caller's cudaStream_t (e.g. the framework's current stream, so scoring is ordered
+ * after the kernels that produced the logits).  The context does not take ownership.  NULL is the legacy default
+ * stream.  No host synchronisation: work already queued on the previous stream is ordered before anything the
+ * context queues on the new one (event wait on the device). */
 ALS_API int als_ctx_set_stream(als_ctx* ctx, void* stream);
 
 /* Last error message of this context (ctx == NULL: of the calling thread). */
@@ -120,8 +129,11 @@ ALS_API int als_score_host(als_ctx* ctx, const void* logits, int dtype,
  * C-order strides, 16-byte alignment; anything else is ALS_ERR_INVALID (never a silent copy).
  * `scores` is HOST f64[N].  The tensor is only borrowed; the caller keeps ownership and
  * runs the deleter.  Synchronous.
+ * Stream exchange (DLPack protocol): device tensors are scored on `stream`, the stream the consumer handed to the
+ * producer's __dlpack__(stream=...) -- the producer has made the data ready there, so no device-wide synchronisation
+ * is needed.  Host tensors ignore it.
  */
-ALS_API int als_score_dlpack(als_ctx* ctx, void* managed, int measure, double* scores);
+ALS_API int als_score_dlpack(als_ctx* ctx, void* managed, int measure, double* scores, void* stream);
 
 /* ---- fused classifier head (replaces Final.call + active_learning.py:234-269) --------- */
 
@@ -189,7 +201,7 @@ ALS_API int als_pool_scores(als_ctx* ctx, float* out, int64_t num_examples);
 
 /*
  * :705-715  filter to `unlabelled`, pick the k = min(M, selection_size) LOWEST confidences.
- *   unlabelled              HOST int64[M], unique ids in [0, num_examples)
+ *   unlabelled              HOST int64[M], unique ids in [0, num_examples) (duplicates are ALS_ERR_INVALID)
  *   out_ids                 HOST int64[min(k, M)], ascending in (confidence, id)
  *   out_unlabelled_conf     HOST f32[M]  == confidence[unlabelled]           (may be NULL)
  *   out_count               number of ids written
@@ -203,12 +215,83 @@ ALS_API int als_pool_select(als_ctx* ctx, const int64_t* unlabelled, int64_t M, 
 /*
  * Device-level selection primitive (block-radix select), also used to merge the
  * per-GPU candidates after the all-gather.
- *   keys  device f32[M];  ids  device int64[M] (unique);  k >= 0
+ *   keys  device f32[M];  ids  device int64[M] (unique: duplicated (key, id) pairs leave output slots unwritten);  k >= 0
  *   out_keys device f32[min(k,M)], out_ids device int64[min(k,M)], ascending in (key, id).
  * Asynchronous on `stream`.
  */
 ALS_API int als_select_smallest(als_ctx* ctx, const float* keys, const int64_t* ids, int64_t M, int64_t k,
                         float* out_keys, int64_t* out_ids, void* stream);
+
+/* ---- multi-GPU: pool sharded by image, one all-gather (no counterpart in the reference) ------------
+ *
+ * The reference scores the whole pool on GPU:0 (active_learning.py:221, :689-700).  Images are independent, so the pool
+ * shards by image: every rank keeps a FULL-SIZE confidence vector (als_pool_begin(num_examples)), scores only the
+ * examples it owns -- the contiguous id range [shard_lo, shard_hi); the ranges of all ranks must tile
+ * [0, num_examples) -- and als_pool_select_global finishes :705-715 for the whole pool:
+ *   1. on the device, one launch: the rank's k lowest (confidence, id) candidates among unlabelled ids it owns, packed
+ *      with its score slice into one record  {lo, n, f32 key[k], i64 id[k], f32 score[max_shard]};
+ *   2. ONE ncclAllGather of the records over NVLink (a few hundred KB at most: latency bound);
+ *   3. on the device, one launch: the other ranks' score slices complete the local confidence vector, the world*k
+ *      candidates are merged with the same block-radix select, unlabelled_confidence is gathered;
+ *   4. ONE device->host copy of {ids, unlabelled_confidence}.
+ * Every rank returns the same result.  Examples nobody visited keep 0.0 and are selected first, like :685/:701-702.
+ */
+
+/* 128-byte NCCL unique id for als_comm_init_rank (rank 0 creates it and hands it to the others out of band). */
+ALS_API int als_comm_unique_id(void* out128);
+
+/* One process per GPU: join a communicator of `world` ranks.  Collective (every rank calls it). */
+ALS_API int als_comm_init_rank(als_ctx* ctx, int rank, int world, const void* unique_id128);
+
+/* One process, n GPUs (the reference's own process model, active_learning.py:221,277): ctxs[i] becomes rank i. */
+ALS_API int als_comm_init_all(als_ctx** ctxs, int n);
+
+ALS_API int als_comm_destroy(als_ctx* ctx);
+
+/*
+ * :705-715 over the sharded pool.  Collective; same arguments on every rank except shard_lo / shard_hi.
+ *   unlabelled       HOST int64[M], unique GLOBAL ids in [0, num_examples)        (same on every rank)
+ *   shard_lo/hi      the id range this rank owns and has scored
+ *   max_shard        upper bound on any rank's shard_hi - shard_lo, identical on all ranks; 0 = ceil(num_examples / world)
+ *   out_*            as als_pool_select
+ * Without a communicator (world 1) it is als_pool_select.  Synchronous.
+ */
+ALS_API int als_pool_select_global(als_ctx* ctx, const int64_t* unlabelled, int64_t M, int64_t selection_size,
+                                   int64_t shard_lo, int64_t shard_hi, int64_t max_shard,
+                                   int64_t* out_ids, float* out_unlabelled_conf, int64_t* out_count);
+
+/* Single-process form: ctxs[i] owns [shard_lo[i], shard_hi[i]); results are read back from ctxs[0]. */
+ALS_API int als_pool_select_global_all(als_ctx** ctxs, int n, const int64_t* unlabelled, int64_t M,
+                                       int64_t selection_size, const int64_t* shard_lo, const int64_t* shard_hi,
+                                       int64_t max_shard, int64_t* out_ids, float* out_unlabelled_conf,
+                                       int64_t* out_count);
+
+/* ---- streamed Monte-Carlo accumulation (extension) --------------------
+ *
+ * als_score takes all T dropout samples at once as [T,N,H,W,C] (948 GB for 2975 images at T = 8).  A producer that
+ * makes one stochastic forward pass at a time -- the reference only builds its dropout under training=True
+ * (models/util/extra_ops.py:137-151, models/enet/enet_modules.py:591-594) -- hands them over one by one instead:
+ * the per-pixel Welford state (running mean per class + summed M2, float32) stays resident in HBM between samples
+ * and [T,...] never materialises.  Results are bit-identical to als_score on the stacked samples.
+ * Bytes per pixel and sample: C*sizeof(elem) read + (C+1)*4 read + (C+1)*4 written (sample 0 skips the state read).
+ * All three run on the context's stream and are asynchronous.
+ */
+
+/* Open an accumulation over a batch of N images [N,H,W,C].  label (optional, device u8[N,H,W]) receives
+ * pseudo_label = argmax of sample 0 (active_learning.py:234-236). */
+ALS_API int als_mc_begin(als_ctx* ctx, int dtype, int64_t N, int64_t H, int64_t W, int64_t C, uint8_t* label);
+
+/* Fold one sample in: logits [N,H,W,C] of the dtype given to als_mc_begin, device (logits_on_host == 0) or host
+ * memory (staged; returns once staged). */
+ALS_API int als_mc_add_sample(als_ctx* ctx, const void* logits, int logits_on_host);
+
+/* Close it: confidence of the predictive mean (entropy / margin / confidence) or 1 - summed variance (variance; needs
+ * >= 2 samples), per-image f64 mean.
+ *   scores         device f64[N], optional
+ *   example_index  HOST int64[N], optional: scatter float32(score) into the pool vector like als_pool_score_batch
+ *   conf_map / mask  optional device [N,H,W] as in als_score */
+ALS_API int als_mc_finish(als_ctx* ctx, int measure, double* scores, const int64_t* example_index, float* conf_map,
+                          uint8_t* mask, float threshold);
 
 /* ---- synthetic pool (bench / tests) ------------------------------------------------ */
 
@@ -228,6 +311,10 @@ ALS_API int als_flush_l2(als_ctx* ctx, void* stream);
 ALS_API int als_describe_launch(als_ctx* ctx, int dtype, int64_t T, int64_t N, int64_t H, int64_t W, int64_t C,
                         int measure, char* name, int* grid, int* block, int* smem_bytes, int* stages,
                         int* tile_pixels);
+
+/* Same for the fused-head kernel als_score_features would launch (needs als_head_prepare). */
+ALS_API int als_describe_head_launch(als_ctx* ctx, int64_t T, int measure, char* name, int* grid, int* block,
+                                     int* smem_bytes);
 
 #ifdef __cplusplus
 }

@@ -8,8 +8,8 @@ hand-written sm_100a CUDA kernels behind a C ABI (include/alscore.h); there is n
 from ._lib import AlscoreUnavailable, LIB_PATH
 from .acquisition import MEASURES, Scorer, default_scorer, measure_id, rank_confidence
 from . import al_loop
-from .distributed import rank_confidence_sharded, shard_bounds
+from .distributed import comm_init_torch, rank_confidence_sharded, rank_confidence_sharded_device, shard_bounds
 
 __all__ = ["al_loop", "AlscoreUnavailable", "LIB_PATH", "MEASURES", "Scorer", "default_scorer", "measure_id",
-           "rank_confidence", "rank_confidence_sharded", "shard_bounds"]
-__version__ = "0.1.0"
+           "comm_init_torch", "rank_confidence", "rank_confidence_sharded", "rank_confidence_sharded_device", "shard_bounds"]
+__version__ = "0.1.1"

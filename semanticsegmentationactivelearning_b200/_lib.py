@@ -36,7 +36,7 @@ SIGNATURES = {
     "als_launch_count": (_i64, [_p]),
     "als_score": (C.c_int, [_p, _p, C.c_int, _i64, _i64, _i64, _i64, _i64, C.c_int, _p, _p, _p, _p, C.c_float, _p]),
     "als_score_host": (C.c_int, [_p, _p, C.c_int, _i64, _i64, _i64, _i64, _i64, C.c_int, _p, _p, _p, _p, C.c_float]),
-    "als_score_dlpack": (C.c_int, [_p, _p, C.c_int, _p]),
+    "als_score_dlpack": (C.c_int, [_p, _p, C.c_int, _p, _p]),
     "als_head_prepare": (C.c_int, [_p, _p, _i64]),
     "als_head_geometry": (C.c_int, [_i64, _p, _p]),
     "als_head_pack_weights": (C.c_int, [_p, _i64, _p, _i64]),
@@ -48,12 +48,28 @@ SIGNATURES = {
     "als_pool_scores": (C.c_int, [_p, _p, _i64]),
     "als_pool_select": (C.c_int, [_p, _p, _i64, _i64, _p, _p, C.POINTER(_i64)]),
     "als_select_smallest": (C.c_int, [_p, _p, _p, _i64, _i64, _p, _p, _p]),
+    "als_comm_unique_id": (C.c_int, [_p]),
+    "als_comm_init_rank": (C.c_int, [_p, C.c_int, C.c_int, _p]),
+    "als_comm_init_all": (C.c_int, [C.POINTER(_p), C.c_int]),
+    "als_comm_destroy": (C.c_int, [_p]),
+    "als_pool_select_global": (C.c_int, [_p, _p, _i64, _i64, _i64, _i64, _i64, _p, _p, C.POINTER(_i64)]),
+    "als_pool_select_global_all": (C.c_int, [C.POINTER(_p), C.c_int, _p, _i64, _i64, _p, _p, _i64, _p, _p,
+                                             C.POINTER(_i64)]),
+    "als_mc_begin": (C.c_int, [_p, C.c_int, _i64, _i64, _i64, _i64, _p]),
+    "als_mc_add_sample": (C.c_int, [_p, _p, C.c_int]),
+    "als_mc_finish": (C.c_int, [_p, C.c_int, _p, _p, _p, _p, C.c_float]),
     "als_synth_logits": (C.c_int, [_p, _p, C.c_int, _i64, _i64, _i64, _i64, _i64, _i64, C.c_uint64, C.c_int, _p]),
     "als_flush_l2": (C.c_int, [_p, _p]),
     "als_describe_launch": (C.c_int, [_p, C.c_int, _i64, _i64, _i64, _i64, _i64, C.c_int, C.c_char_p,
                                       C.POINTER(C.c_int), C.POINTER(C.c_int), C.POINTER(C.c_int),
                                       C.POINTER(C.c_int), C.POINTER(C.c_int)]),
+    "als_describe_head_launch": (C.c_int, [_p, _i64, C.c_int, C.c_char_p, C.POINTER(C.c_int), C.POINTER(C.c_int),
+                                           C.POINTER(C.c_int)]),
 }
+
+ALS_VERSION = 110
+# `stream` argument meaning "the context's stream" (include/alscore.h: ALS_STREAM_CTX); 0 / None is the legacy default stream
+ALS_STREAM_CTX = C.c_void_p(-1)
 
 _lib = None
 
@@ -70,6 +86,7 @@ def load() -> C.CDLL:
         raise AlscoreUnavailable(
             "%s not found: build it with `python -m semanticsegmentationactivelearning_b200.build` "
             "(needs nvcc; the pool-scoring path has no CPU fallback)" % LIB_PATH)
+    _point_at_nccl()
     try:
         lib = C.CDLL(LIB_PATH)
     except OSError as e:  # pragma: no cover
@@ -80,6 +97,23 @@ def load() -> C.CDLL:
         fn.argtypes = args
     _lib = lib
     return lib
+
+
+def _point_at_nccl() -> None:
+    """The multi-GPU exchange binds NCCL at run time (csrc/comm.cu): a copy the process already holds wins, else
+    ALS_NCCL_LIB, else the loader path.  Default ALS_NCCL_LIB to the wheel torch ships (nvidia-nccl-cu12)."""
+    if os.environ.get("ALS_NCCL_LIB"):
+        return
+    try:
+        import importlib.util
+        spec = importlib.util.find_spec("nvidia.nccl")
+        for root in (spec.submodule_search_locations if spec else []):
+            cand = os.path.join(root, "lib", "libnccl.so.2")
+            if os.path.exists(cand):
+                os.environ["ALS_NCCL_LIB"] = cand
+                return
+    except Exception:  # pragma: no cover
+        pass
 
 
 def last_error(ctx=None) -> str:

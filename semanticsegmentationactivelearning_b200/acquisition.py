@@ -98,11 +98,9 @@ class Scorer:
         self._lib = lib
         self._ctx = C.c_void_p()
         _lib.check(lib.als_ctx_create(self.device, C.byref(self._ctx)))
-        self._stream = None
-        if use_torch_stream and torch is not None and torch.cuda.is_available():
-            # order our kernels after whatever produced the logits on torch's current stream
-            self._stream = int(torch.cuda.current_stream(self.device).cuda_stream)
-            _lib.check(lib.als_ctx_set_stream(self._ctx, C.c_void_p(self._stream)), self._ctx)
+        self._stream = None                 # None: the context's own (non-blocking) stream
+        self._follow_torch = bool(use_torch_stream and torch is not None and torch.cuda.is_available())
+        self._sync_stream()
 
     # -- lifetime ---------------------------------------------------------------------------
     def close(self) -> None:
@@ -130,6 +128,24 @@ class Scorer:
     def _check(self, rc: int) -> None:
         _lib.check(rc, self._ctx)
 
+    def _sync_stream(self) -> None:
+        """Entries without a `stream` argument (pool_*, mc_*, host staging) run on the context's stream: keep that
+        equal to torch's CURRENT stream, so they are ordered after the producer of the logits and before any torch
+        consumer of their results, also under ``with torch.cuda.stream(side)``.  (The library orders the new stream
+        behind the work already queued on the old one.)"""
+        if not self._follow_torch:
+            return
+        cur = int(_torch().cuda.current_stream(self.device).cuda_stream)
+        if cur != self._stream:
+            self._check(self._lib.als_ctx_set_stream(self._ctx, C.c_void_p(cur)))
+            self._stream = cur
+
+    def _stream_arg(self, device=None):
+        """`stream` argument of the device entries: torch's current stream on the tensor's device (handle 0 is the
+        legacy default stream, which is what torch's default stream is)."""
+        torch = _torch()
+        return C.c_void_p(int(torch.cuda.current_stream(self.device if device is None else device).cuda_stream))
+
     # -- graph-level boundary (active_learning.py:234-269) ---------------------------------
     def score(self, logits, measure: str = "entropy", *, dtype: Optional[str] = None, out=None):
         """pseudo_mean_confidence: per-image f64 mean confidence.
@@ -139,6 +155,7 @@ class Scorer:
         m = measure_id(measure)
         lg = _Logits(logits, dtype)
         if lg.on_host:
+            self._sync_stream()
             scores = np.empty(lg.N, dtype=np.float64)
             self._check(self._lib.als_score_host(self._ctx, lg.ptr, lg.dtype, lg.T, lg.N, lg.H, lg.W, lg.C, m,
                                                  scores.ctypes.data, None, None, None, 0.0))
@@ -146,9 +163,8 @@ class Scorer:
         torch = _torch()
         if out is None:
             out = torch.empty(lg.N, dtype=torch.float64, device=logits.device)
-        stream = torch.cuda.current_stream(logits.device).cuda_stream
         self._check(self._lib.als_score(self._ctx, lg.ptr, lg.dtype, lg.T, lg.N, lg.H, lg.W, lg.C, m,
-                                        out.data_ptr(), None, None, None, 0.0, C.c_void_p(stream)))
+                                        out.data_ptr(), None, None, None, 0.0, self._stream_arg(logits.device)))
         return out
 
     def pseudo_annotation(self, logits, measure: str = "entropy", threshold: float = 0.9, *,
@@ -162,6 +178,7 @@ class Scorer:
         lg = _Logits(logits, dtype)
         shp = (lg.N, lg.H, lg.W)
         if lg.on_host:
+            self._sync_stream()
             conf = np.empty(shp, np.float32)
             label = np.empty(shp, np.uint8) if want_label else None
             mask = np.empty(shp, np.uint8) if want_mask else None
@@ -182,11 +199,10 @@ class Scorer:
                 label = torch.empty(shp, dtype=torch.uint8, device=dev) if want_label else None
                 mask = torch.empty(shp, dtype=torch.uint8, device=dev) if want_mask else None
                 scores = torch.empty(lg.N, dtype=torch.float64, device=dev)
-            stream = torch.cuda.current_stream(dev).cuda_stream
             self._check(self._lib.als_score(
                 self._ctx, lg.ptr, lg.dtype, lg.T, lg.N, lg.H, lg.W, lg.C, m, scores.data_ptr(), conf.data_ptr(),
                 label.data_ptr() if want_label else None, mask.data_ptr() if want_mask else None, float(threshold),
-                C.c_void_p(stream)))
+                self._stream_arg(dev)))
         return {"pseudo_confidence": conf, "pseudo_mean_confidence": scores, "pseudo_label": label,
                 "pseudo_mask": mask}
 
@@ -224,9 +240,8 @@ class Scorer:
         torch, (t, n, h, w) = self._features(features)
         if out is None:
             out = torch.empty(n, dtype=torch.float64, device=features.device)
-        stream = torch.cuda.current_stream(features.device).cuda_stream
         self._check(self._lib.als_score_features(self._ctx, features.data_ptr(), t, n, h, w, m, out.data_ptr(), None, None,
-                                                 None, 0.0, C.c_void_p(stream)))
+                                                 None, 0.0, self._stream_arg(features.device)))
         return out
 
     def pseudo_annotation_features(self, features, measure: str = "entropy", threshold: float = 0.9):
@@ -239,10 +254,9 @@ class Scorer:
         label = torch.empty(shp, dtype=torch.uint8, device=dev)
         mask = torch.empty(shp, dtype=torch.uint8, device=dev)
         scores = torch.empty(n, dtype=torch.float64, device=dev)
-        stream = torch.cuda.current_stream(dev).cuda_stream
         self._check(self._lib.als_score_features(self._ctx, features.data_ptr(), t, n, h, w, m, scores.data_ptr(),
                                                  conf.data_ptr(), label.data_ptr(), mask.data_ptr(), float(threshold),
-                                                 C.c_void_p(stream)))
+                                                 self._stream_arg(dev)))
         return {"pseudo_confidence": conf, "pseudo_mean_confidence": scores, "pseudo_label": label, "pseudo_mask": mask}
 
     def pool_score_features_batch(self, features, batch_indices, measure: str = "entropy") -> None:
@@ -267,6 +281,7 @@ class Scorer:
         if idx.shape != (b,):
             raise ValueError("batch_indices must have one entry per image (%d), got shape %s" % (b, idx.shape))
         self._keep = features
+        self._sync_stream()
         self._check(self._lib.als_pool_score_features_batch(self._ctx, ptr, 1 if on_host else 0, int(t), int(b), int(h),
                                                             int(w), m, idx.ctypes.data))
 
@@ -274,7 +289,21 @@ class Scorer:
         """Score any ``__dlpack__`` producer (TF >= 2.2, CuPy, JAX, NumPy, torch): device tensors
         zero-copy, host tensors staged.  Returns NumPy f64[N]."""
         m = measure_id(measure)
-        capsule = producer.__dlpack__() if hasattr(producer, "__dlpack__") else producer
+        self._sync_stream()
+        stream_arg = _lib.ALS_STREAM_CTX
+        if hasattr(producer, "__dlpack__"):
+            # DLPack stream exchange: hand the producer the stream we will score on, it makes the data ready there.
+            # (CUDA convention: 1 = legacy default stream, 2 = per-thread default, larger = a cudaStream_t handle.)
+            on_cuda = hasattr(producer, "__dlpack_device__") and producer.__dlpack_device__()[0] in (2, 13)
+            if on_cuda:
+                # without a torch stream to follow, score on the legacy default stream (handle 0) and say so
+                h = self._stream if self._stream is not None else 0
+                capsule = producer.__dlpack__(stream=h if h > 2 else 1)
+                stream_arg = C.c_void_p(h)
+            else:
+                capsule = producer.__dlpack__()
+        else:
+            capsule = producer
         api = C.pythonapi
         api.PyCapsule_GetPointer.restype = C.c_void_p
         api.PyCapsule_GetPointer.argtypes = [C.py_object, C.c_char_p]
@@ -291,7 +320,7 @@ class Scorer:
         n = C.c_int64.from_address(shape_ptr + 8 * (ndim - 4)).value
         scores = np.empty(max(n, 0), np.float64)
         try:
-            self._check(self._lib.als_score_dlpack(self._ctx, managed, m, scores.ctypes.data))
+            self._check(self._lib.als_score_dlpack(self._ctx, managed, m, scores.ctypes.data, stream_arg))
         finally:
             # consumer protocol: mark the capsule used and run the producer's deleter
             api.PyCapsule_SetName(capsule, _USED_NAME)
@@ -302,6 +331,7 @@ class Scorer:
 
     # -- loop-level boundary (rank_confidence, active_learning.py:682-715) ------------------
     def pool_begin(self, num_examples: int) -> None:
+        self._sync_stream()
         self._check(self._lib.als_pool_begin(self._ctx, int(num_examples)))
 
     def pool_score_batch(self, logits, batch_indices, measure: str = "entropy", *, dtype: Optional[str] = None) -> None:
@@ -310,11 +340,13 @@ class Scorer:
         idx = np.ascontiguousarray(np.asarray(batch_indices, dtype=np.int64))
         if idx.shape != (lg.N,):
             raise ValueError("batch_indices must have one entry per image (%d), got shape %s" % (lg.N, idx.shape))
+        self._sync_stream()
         self._check(self._lib.als_pool_score_batch(self._ctx, lg.ptr, 1 if lg.on_host else 0, lg.dtype, lg.T, lg.N,
                                                    lg.H, lg.W, lg.C, m, idx.ctypes.data))
 
     def pool_scores(self, num_examples: int) -> np.ndarray:
         out = np.empty(int(num_examples), np.float32)
+        self._sync_stream()
         self._check(self._lib.als_pool_scores(self._ctx, out.ctypes.data, int(num_examples)))
         return out
 
@@ -326,9 +358,113 @@ class Scorer:
         ids = np.empty(k, np.int64)
         conf = np.empty(unl.size, np.float32)
         cnt = C.c_int64(0)
+        self._sync_stream()
         self._check(self._lib.als_pool_select(self._ctx, unl.ctypes.data, unl.size, int(selection_size),
                                               ids.ctypes.data, conf.ctypes.data, C.byref(cnt)))
         return ids[:cnt.value], conf
+
+    # -- multi-GPU: pool sharded by image (csrc/comm.cu) ------------------------------------------------
+    def comm_init(self, rank: int, world: int, unique_id: bytes) -> None:
+        """Join the NCCL communicator of a sharded pool pass (one process per GPU).  `unique_id` is the 128-byte id
+        rank 0 got from ``comm_unique_id()`` and passed around out of band (e.g. a torch.distributed broadcast)."""
+        if len(unique_id) != 128:
+            raise ValueError("unique_id must be 128 bytes")
+        buf = C.create_string_buffer(bytes(unique_id), 128)
+        self._check(self._lib.als_comm_init_rank(self._ctx, int(rank), int(world), buf))
+
+    @staticmethod
+    def comm_unique_id() -> bytes:
+        buf = C.create_string_buffer(128)
+        _lib.check(_lib.load().als_comm_unique_id(buf))
+        return buf.raw
+
+    @staticmethod
+    def comm_init_all(scorers: Sequence["Scorer"]) -> None:
+        """Single-process form: scorers[i] (one per GPU) becomes rank i of one communicator (ncclCommInitAll)."""
+        arr = (C.c_void_p * len(scorers))(*[s._ctx.value for s in scorers])
+        _lib.check(_lib.load().als_comm_init_all(arr, len(scorers)), scorers[0]._ctx)
+
+    def pool_select_global(self, unlabelled, selection_size: int, shard: Tuple[int, int], max_shard: int = 0):
+        """:705-715 over the pool sharded across the communicator: this rank owns (and has scored) the example ids
+        [shard[0], shard[1]).  Collective; returns the same (low_conf_examples, unlabelled_confidence) on every rank.
+        On the device: local k candidates -> ONE ncclAllGather -> merge; one device->host copy."""
+        unl = np.ascontiguousarray(np.asarray(unlabelled, dtype=np.int64))
+        if unl.ndim != 1:
+            raise ValueError("unlabelled must be a 1-D index array")
+        k = int(max(0, min(int(selection_size), unl.size)))
+        ids = np.empty(k, np.int64)
+        conf = np.empty(unl.size, np.float32)
+        cnt = C.c_int64(0)
+        self._sync_stream()
+        self._check(self._lib.als_pool_select_global(self._ctx, unl.ctypes.data, unl.size, int(selection_size),
+                                                     int(shard[0]), int(shard[1]), int(max_shard), ids.ctypes.data,
+                                                     conf.ctypes.data, C.byref(cnt)))
+        return ids[:cnt.value], conf
+
+    @staticmethod
+    def pool_select_global_all(scorers: Sequence["Scorer"], unlabelled, selection_size: int,
+                               shards: Sequence[Tuple[int, int]], max_shard: int = 0):
+        """Single-process form of pool_select_global over scorers joined by comm_init_all."""
+        unl = np.ascontiguousarray(np.asarray(unlabelled, dtype=np.int64))
+        k = int(max(0, min(int(selection_size), unl.size)))
+        ids = np.empty(k, np.int64)
+        conf = np.empty(unl.size, np.float32)
+        cnt = C.c_int64(0)
+        n = len(scorers)
+        arr = (C.c_void_p * n)(*[s._ctx.value for s in scorers])
+        lo = np.ascontiguousarray([int(s[0]) for s in shards], dtype=np.int64)
+        hi = np.ascontiguousarray([int(s[1]) for s in shards], dtype=np.int64)
+        for s in scorers:
+            s._sync_stream()
+        _lib.check(_lib.load().als_pool_select_global_all(arr, n, unl.ctypes.data, unl.size, int(selection_size),
+                                                          lo.ctypes.data, hi.ctypes.data, int(max_shard), ids.ctypes.data,
+                                                          conf.ctypes.data, C.byref(cnt)), scorers[0]._ctx)
+        return ids[:cnt.value], conf
+
+    # -- streamed Monte-Carlo accumulation (one dropout pass at a time; Welford state stays in HBM) -------
+    def mc_begin(self, shape, dtype: str = "float32", label=None) -> None:
+        """Open an accumulation over a batch [N,H,W,C].  `label` (optional CUDA uint8 [N,H,W]) receives the argmax of
+        sample 0.  Then mc_add_sample(logits_t) per stochastic forward pass and mc_finish(measure)."""
+        n, h, w, c = (int(v) for v in shape)
+        self._sync_stream()
+        self._mc_shape = (n, h, w, c)
+        self._check(self._lib.als_mc_begin(self._ctx, _lib.ALS_F32 if dtype == "float32" else _lib.ALS_BF16, n, h, w, c,
+                                           None if label is None else label.data_ptr()))
+        self._mc_dtype = _lib.ALS_F32 if dtype == "float32" else _lib.ALS_BF16
+        self._mc_label = label
+
+    def mc_add_sample(self, logits, *, dtype: Optional[str] = None) -> None:
+        lg = _Logits(logits, dtype)
+        if lg.T != 1 or (lg.N, lg.H, lg.W, lg.C) != self._mc_shape or lg.dtype != self._mc_dtype:
+            raise ValueError("sample must be [N,H,W,C] = %s of the dtype given to mc_begin" % (self._mc_shape,))
+        self._sync_stream()
+        self._keep = logits
+        self._check(self._lib.als_mc_add_sample(self._ctx, lg.ptr, 1 if lg.on_host else 0))
+
+    def mc_finish(self, measure: str = "variance", *, batch_indices=None, threshold: float = 0.9, want_maps: bool = False):
+        """Close the accumulation.  Returns pseudo_mean_confidence (torch f64 CUDA [N]); with ``batch_indices`` the
+        scores are also scattered into the pool vector (like pool_score_batch); with ``want_maps`` returns the dict of
+        pseudo_annotation() (pseudo_label is the tensor given to mc_begin)."""
+        m = measure_id(measure)
+        torch = _torch()
+        n, h, w, c = self._mc_shape
+        dev = torch.device("cuda", self.device)
+        scores = torch.empty(n, dtype=torch.float64, device=dev)
+        conf = torch.empty((n, h, w), dtype=torch.float32, device=dev) if want_maps else None
+        mask = torch.empty((n, h, w), dtype=torch.uint8, device=dev) if want_maps else None
+        idx = None
+        if batch_indices is not None:
+            idx = np.ascontiguousarray(np.asarray(batch_indices, dtype=np.int64))
+            if idx.shape != (n,):
+                raise ValueError("batch_indices must have one entry per image (%d), got shape %s" % (n, idx.shape))
+        self._sync_stream()
+        self._check(self._lib.als_mc_finish(self._ctx, m, scores.data_ptr(), None if idx is None else idx.ctypes.data,
+                                            None if conf is None else conf.data_ptr(),
+                                            None if mask is None else mask.data_ptr(), float(threshold)))
+        if want_maps:
+            return {"pseudo_confidence": conf, "pseudo_mean_confidence": scores, "pseudo_label": self._mc_label,
+                    "pseudo_mask": mask}
+        return scores
 
     # -- device primitives --------------------------------------------------------------------
     def select_smallest(self, keys, ids, k: int):
@@ -343,9 +479,8 @@ class Scorer:
         kk = max(0, min(int(k), M))
         ok = torch.empty(kk, dtype=torch.float32, device=keys.device)
         oi = torch.empty(kk, dtype=torch.int64, device=keys.device)
-        stream = torch.cuda.current_stream(keys.device).cuda_stream
         self._check(self._lib.als_select_smallest(self._ctx, keys.data_ptr(), ids.data_ptr(), M, int(k),
-                                                  ok.data_ptr(), oi.data_ptr(), C.c_void_p(stream)))
+                                                  ok.data_ptr(), oi.data_ptr(), self._stream_arg(keys.device)))
         return ok, oi
 
     def synth_logits(self, T: int, n0: int, n_imgs: int, H: int, W: int, C_: int, *, dtype: str = "float32",
@@ -355,15 +490,12 @@ class Scorer:
         tdt = {"float32": torch.float32, "bfloat16": torch.bfloat16}[dtype]
         if out is None:
             out = torch.empty((T, n_imgs, H, W, C_), dtype=tdt, device=torch.device("cuda", self.device))
-        stream = torch.cuda.current_stream(out.device).cuda_stream
         self._check(self._lib.als_synth_logits(self._ctx, out.data_ptr(), _lib.ALS_F32 if dtype == "float32" else _lib.ALS_BF16,
-                                               T, n0, n_imgs, H, W, C_, seed, 1 if T > 1 else 0, C.c_void_p(stream)))
+                                               T, n0, n_imgs, H, W, C_, seed, 1 if T > 1 else 0, self._stream_arg(out.device)))
         return out[0] if (T == 1 and squeeze_t and out.dim() == 5) else out
 
     def flush_l2(self) -> None:
-        torch = _torch()
-        stream = torch.cuda.current_stream(self.device).cuda_stream
-        self._check(self._lib.als_flush_l2(self._ctx, C.c_void_p(stream)))
+        self._check(self._lib.als_flush_l2(self._ctx, self._stream_arg()))
 
     def describe_launch(self, dtype: str, T: int, N: int, H: int, W: int, C_: int, measure: str) -> dict:
         name = C.create_string_buffer(128)
@@ -373,6 +505,15 @@ class Scorer:
                                                   C.byref(st), C.byref(tp)))
         return {"kernel": name.value.decode(), "grid": g.value, "block": b.value, "smem_bytes": s.value,
                 "stages": st.value, "tile_pixels": tp.value}
+
+    def describe_head_launch(self, T: int, measure: str) -> dict:
+        """The fused-head kernel score_features would launch (after prepare_head), from the library's own plan."""
+        name = C.create_string_buffer(128)
+        g, b, s = (C.c_int() for _ in range(3))
+        self._check(self._lib.als_describe_head_launch(self._ctx, int(T), measure_id(measure), name, C.byref(g), C.byref(b),
+                                                       C.byref(s)))
+        return {"kernel": name.value.decode(), "grid": g.value, "block": b.value, "smem_bytes": s.value,
+                "stages": None, "tile_pixels": 512}
 
 
 def head_mma_flops_per_pixel(num_classes: int) -> float:

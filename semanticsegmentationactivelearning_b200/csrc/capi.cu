@@ -10,8 +10,9 @@
 #include <string>
 #include <vector>
 
-#include "../../include/alscore.h"
+#include "ctx.h"
 #include "head.cuh"
+#include "mc.cuh"
 #include "score.cuh"
 #include "select.cuh"
 #include "synth.cuh"
@@ -34,55 +35,7 @@ enum { kAlsDLFloat = 2, kAlsDLBfloat = 4 };
 
 static thread_local std::string g_tls_error;
 
-struct als_ctx {
-  int device = 0;
-  int num_sms = 148;
-  int max_smem = 227 * 1024;
-  cudaStream_t stream = nullptr;
-  bool owns_stream = true;
-  cudaStream_t copy_stream = nullptr;
-  std::string error;
-  int64_t launches = 0;
-  // per-image fixed-point accumulators
-  long long* acc = nullptr;
-  unsigned int* flags = nullptr;
-  unsigned long long* tile_counter = nullptr;
-  int64_t acc_cap = 0;
-  // device scratch for scores / indices
-  double* scores_dev = nullptr;
-  int64_t scores_cap = 0;
-  long long* index_dev = nullptr;
-  int64_t index_cap = 0;
-  // pool state (rank_confidence)
-  float* pool32 = nullptr;
-  int64_t pool_n = -1;
-  int64_t pool_cap = 0;
-  // selection scratch
-  long long* sel_ids = nullptr;
-  float* sel_keys = nullptr;
-  float* sel_tmp_keys = nullptr;
-  long long* sel_tmp_ids = nullptr;
-  float* sel_out_keys = nullptr;
-  long long* sel_out_ids = nullptr;
-  int64_t sel_cap = 0;
-  // host -> device staging (double buffered)
-  void* stage[2] = {nullptr, nullptr};
-  size_t stage_cap = 0;
-  cudaEvent_t ev_copied[2] = {nullptr, nullptr};
-  cudaEvent_t ev_scored[2] = {nullptr, nullptr};
-  int stage_next = 0;
-  // per-pixel output staging for the host path
-  void* maps_dev = nullptr;
-  size_t maps_cap = 0;
-  // fused classifier head: packed split-TF32 weights of `Final` (als_head_prepare)
-  float* head_weights = nullptr;
-  int64_t head_C = 0;
-  // L2 flush scratch
-  void* flush_buf = nullptr;
-  size_t flush_bytes = 0;
-};
-
-namespace {
+namespace als {
 
 int fail(als_ctx* ctx, int code, const char* fmt, ...) {
   char buf[512];
@@ -95,87 +48,46 @@ int fail(als_ctx* ctx, int code, const char* fmt, ...) {
   return code;
 }
 
-#define ALS_CUDA(ctx, call)                                                                             \
-  do {                                                                                                  \
-    cudaError_t _e = (call);                                                                            \
-    if (_e != cudaSuccess) {                                                                            \
-      (void)cudaGetLastError();                                                                         \
-      return fail(ctx, _e == cudaErrorMemoryAllocation ? ALS_ERR_NOMEM : ALS_ERR_CUDA, "%s failed: %s", \
-                  #call, cudaGetErrorString(_e));                                                       \
-    }                                                                                                   \
-  } while (0)
-
-#define ALS_TRY(expr)            \
-  do {                           \
-    int _rc = (expr);            \
-    if (_rc != ALS_OK) return _rc; \
-  } while (0)
-
-struct DeviceGuard {
-  int prev = -1;
-  explicit DeviceGuard(int dev) {
-    cudaGetDevice(&prev);
-    if (prev != dev) cudaSetDevice(dev);
-    else prev = -1;
-  }
-  ~DeviceGuard() {
-    if (prev >= 0) cudaSetDevice(prev);
-  }
-};
-
-template <typename T>
-int grow(als_ctx* ctx, T** ptr, int64_t* cap, int64_t need, bool zero) {
+int grow_bytes(als_ctx* ctx, void** ptr, size_t* cap, size_t need) {
   if (need <= *cap) return ALS_OK;
-  int64_t n = *cap > 0 ? *cap : 1024;
+  size_t n = *cap ? *cap : 4096;
   while (n < need) n *= 2;
   ALS_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
   if (*ptr) ALS_CUDA(ctx, cudaFree(*ptr));
   *ptr = nullptr;
   *cap = 0;
-  ALS_CUDA(ctx, cudaMalloc(reinterpret_cast<void**>(ptr), static_cast<size_t>(n) * sizeof(T)));
-  if (zero) ALS_CUDA(ctx, cudaMemsetAsync(*ptr, 0, static_cast<size_t>(n) * sizeof(T), ctx->stream));
+  ALS_CUDA(ctx, cudaMalloc(ptr, n));
   *cap = n;
   return ALS_OK;
 }
 
-int grow_bytes(als_ctx* ctx, void** ptr, size_t* cap, size_t need) {
+int grow_pinned(als_ctx* ctx, void** ptr, size_t* cap, size_t need) {
   if (need <= *cap) return ALS_OK;
+  size_t n = *cap ? *cap : 4096;
+  while (n < need) n *= 2;
   ALS_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
-  if (*ptr) ALS_CUDA(ctx, cudaFree(*ptr));
+  if (*ptr) ALS_CUDA(ctx, cudaFreeHost(*ptr));
   *ptr = nullptr;
   *cap = 0;
-  ALS_CUDA(ctx, cudaMalloc(ptr, need));
-  *cap = need;
+  ALS_CUDA(ctx, cudaMallocHost(ptr, n));
+  *cap = n;
   return ALS_OK;
 }
 
-int ceil_log2_ll(long long v) {
-  int b = 0;
-  while ((1ll << b) < v) ++b;
-  return b;
+cudaStream_t resolve_stream(als_ctx* ctx, void* stream) {
+  return stream == ALS_STREAM_CTX ? ctx->stream : static_cast<cudaStream_t>(stream);
 }
 
-struct Shape {
-  int64_t T, N, H, W, C;
-  int64_t P() const { return H * W; }
-  int64_t elems() const { return T * N * H * W * C; }
-};
-
-int check_common(als_ctx* ctx, const void* logits, int dtype, const Shape& s, int measure, bool want_label) {
-  if (!ctx) return fail(nullptr, ALS_ERR_INVALID, "context is NULL");
-  if (dtype != ALS_F32 && dtype != ALS_BF16) return fail(ctx, ALS_ERR_INVALID, "logits dtype must be float32 or bfloat16");
-  if (measure < ALS_ENTROPY || measure > ALS_VARIANCE)
-    return fail(ctx, ALS_ERR_UNSUPPORTED, "Uncertainty function not implemented.");
-  if (s.T < 1 || s.N < 0 || s.H < 1 || s.W < 1) return fail(ctx, ALS_ERR_INVALID, "bad logits shape [T=%lld,N=%lld,H=%lld,W=%lld,C=%lld]",
-                                                            (long long)s.T, (long long)s.N, (long long)s.H, (long long)s.W, (long long)s.C);
-  if (s.C < 2) return fail(ctx, ALS_ERR_INVALID, "need at least 2 classes, got C=%lld", (long long)s.C);
-  if (s.C > 65536) return fail(ctx, ALS_ERR_INVALID, "C=%lld is too large", (long long)s.C);
-  if (measure == ALS_VARIANCE && s.T < 2) return fail(ctx, ALS_ERR_INVALID, "measure 'variance' needs T >= 2 Monte-Carlo samples");
-  if (want_label && s.C > 256) return fail(ctx, ALS_ERR_INVALID, "uint8 pseudo_label needs C <= 256");
-  if (s.P() > (1ll << 40)) return fail(ctx, ALS_ERR_INVALID, "image too large");
-  if (s.N > 0x7fffffff) return fail(ctx, ALS_ERR_INVALID, "too many images in one call");
-  if (s.N > 0 && !logits) return fail(ctx, ALS_ERR_INVALID, "logits pointer is NULL");
-  if (reinterpret_cast<uintptr_t>(logits) % 16 != 0) return fail(ctx, ALS_ERR_INVALID, "logits must be 16-byte aligned");
+// The accumulators / flags / tile counter are one set per context: a launch sequence on another stream than the
+// previous one first waits for that one's end-of-sequence event.
+int scratch_begin(als_ctx* ctx, cudaStream_t st) {
+  if (ctx->scratch_used && st != ctx->scratch_stream) ALS_CUDA(ctx, cudaStreamWaitEvent(st, ctx->ev_scratch, 0));
+  return ALS_OK;
+}
+int scratch_end(als_ctx* ctx, cudaStream_t st) {
+  ALS_CUDA(ctx, cudaEventRecord(ctx->ev_scratch, st));
+  ctx->scratch_stream = st;
+  ctx->scratch_used = true;
   return ALS_OK;
 }
 
@@ -194,6 +106,51 @@ int check_device_ptr(als_ctx* ctx, const void* p, const char* what) {
   return ALS_OK;
 }
 
+}  // namespace als
+
+using als::check_device_ptr;
+using als::DeviceGuard;
+using als::fail;
+using als::grow;
+using als::grow_bytes;
+using als::grow_pinned;
+using als::resolve_stream;
+using als::scratch_begin;
+using als::scratch_end;
+
+namespace {
+
+int ceil_log2_ll(long long v) {
+  int b = 0;
+  while ((1ll << b) < v) ++b;
+  return b;
+}
+
+struct Shape {
+  int64_t T, N, H, W, C;
+  int64_t P() const { return H * W; }
+  int64_t elems() const { return T * N * H * W * C; }
+};
+
+int check_common(als_ctx* ctx, const void* logits, int dtype, const Shape& s, int measure, bool want_label) {
+  // (no alignment requirement: host logits are staged into an aligned buffer, misaligned device logits take the
+  //  generic kernel, see score_device)
+  if (!ctx) return fail(nullptr, ALS_ERR_INVALID, "context is NULL");
+  if (dtype != ALS_F32 && dtype != ALS_BF16) return fail(ctx, ALS_ERR_INVALID, "logits dtype must be float32 or bfloat16");
+  if (measure < ALS_ENTROPY || measure > ALS_VARIANCE)
+    return fail(ctx, ALS_ERR_UNSUPPORTED, "Uncertainty function not implemented.");
+  if (s.T < 1 || s.N < 0 || s.H < 1 || s.W < 1) return fail(ctx, ALS_ERR_INVALID, "bad logits shape [T=%lld,N=%lld,H=%lld,W=%lld,C=%lld]",
+                                                            (long long)s.T, (long long)s.N, (long long)s.H, (long long)s.W, (long long)s.C);
+  if (s.C < 2) return fail(ctx, ALS_ERR_INVALID, "need at least 2 classes, got C=%lld", (long long)s.C);
+  if (s.C > 65536) return fail(ctx, ALS_ERR_INVALID, "C=%lld is too large", (long long)s.C);
+  if (measure == ALS_VARIANCE && s.T < 2) return fail(ctx, ALS_ERR_INVALID, "measure 'variance' needs T >= 2 Monte-Carlo samples");
+  if (want_label && s.C > 256) return fail(ctx, ALS_ERR_INVALID, "uint8 pseudo_label needs C <= 256");
+  if (s.P() > (1ll << 40)) return fail(ctx, ALS_ERR_INVALID, "image too large");
+  if (s.N > 0x7fffffff) return fail(ctx, ALS_ERR_INVALID, "too many images in one call");
+  if (s.N > 0 && !logits) return fail(ctx, ALS_ERR_INVALID, "logits pointer is NULL");
+  return ALS_OK;
+}
+
 // Core: device logits -> fixed-point sums -> finalize.  scores64 / pool scatter optional.
 int score_device(als_ctx* ctx, const void* logits, int dtype, const Shape& s, int measure, double* scores64,
                  float* pool32, const long long* example_index_dev, int64_t num_examples, float* conf_map,
@@ -202,9 +159,11 @@ int score_device(als_ctx* ctx, const void* logits, int dtype, const Shape& s, in
   const long long P = s.P();
   const int es = dtype == ALS_F32 ? 4 : 2;
   const long long sample_stride = s.N * P * s.C;
-  const bool aligned = (s.T == 1) || ((sample_stride * es) % 16 == 0);
+  // the bulk copies need 16-byte aligned sample planes; anything else runs the generic kernel (same results)
+  const bool aligned = (reinterpret_cast<uintptr_t>(logits) % 16 == 0) && ((s.T == 1) || ((sample_stride * es) % 16 == 0));
   als::LaunchPlan plan = als::plan_score(dtype, static_cast<int>(s.C), measure, static_cast<int>(s.T), s.N * P, aligned,
                                          ctx->num_sms, ctx->max_smem);
+  ALS_TRY(scratch_begin(ctx, stream));
   int shift = 62 - ceil_log2_ll(P);
   if (shift > 44) shift = 44;
   als::ScoreParams p{};
@@ -230,13 +189,15 @@ int score_device(als_ctx* ctx, const void* logits, int dtype, const Shape& s, in
   ALS_CUDA(ctx, als::launch_finalize(ctx->acc, ctx->acc_cap, ctx->flags, ctx->tile_counter, static_cast<int>(s.N), ldexp(1.0, -shift) / static_cast<double>(P),
                                      scores64, pool32, example_index_dev, num_examples, stream));
   ctx->launches += 2;
-  return ALS_OK;
+  return scratch_end(ctx, stream);
 }
 
 int ensure_acc(als_ctx* ctx, int64_t n) {
   if (n <= ctx->acc_cap) return ALS_OK;
   int64_t cap = ctx->acc_cap > 0 ? ctx->acc_cap : 1024;
   while (cap < n) cap *= 2;
+  // the old set may still be in use on whichever stream ran the last launch sequence
+  if (ctx->scratch_used) ALS_CUDA(ctx, cudaEventSynchronize(ctx->ev_scratch));
   ALS_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
   if (ctx->acc) ALS_CUDA(ctx, cudaFree(ctx->acc));
   if (ctx->flags) ALS_CUDA(ctx, cudaFree(ctx->flags));
@@ -245,8 +206,11 @@ int ensure_acc(als_ctx* ctx, int64_t n) {
   ctx->acc_cap = 0;
   ALS_CUDA(ctx, cudaMalloc(reinterpret_cast<void**>(&ctx->acc), static_cast<size_t>(cap) * als::kAccReplicas * sizeof(long long)));
   ALS_CUDA(ctx, cudaMalloc(reinterpret_cast<void**>(&ctx->flags), static_cast<size_t>(cap) * sizeof(unsigned int)));
+  // zero them before any stream can launch on them (cudaMemset on device memory is asynchronous to the host and
+  // a non-blocking stream does not order behind the NULL stream: wait for it here, this is a rare grow)
   ALS_CUDA(ctx, cudaMemset(ctx->acc, 0, static_cast<size_t>(cap) * als::kAccReplicas * sizeof(long long)));
   ALS_CUDA(ctx, cudaMemset(ctx->flags, 0, static_cast<size_t>(cap) * sizeof(unsigned int)));
+  ALS_CUDA(ctx, cudaDeviceSynchronize());
   ctx->acc_cap = cap;
   return ALS_OK;
 }
@@ -276,10 +240,16 @@ int stage_chunk(als_ctx* ctx, const unsigned char* host, const Shape& s, int es,
   const size_t img_bytes = static_cast<size_t>(s.P()) * s.C * es;
   // the previous user of this buffer must have been scored
   ALS_CUDA(ctx, cudaStreamWaitEvent(ctx->copy_stream, ctx->ev_scored[b], 0));
-  for (int64_t t = 0; t < s.T; ++t) {
-    const unsigned char* src = host + (static_cast<size_t>(t) * s.N + n0) * img_bytes;
-    unsigned char* dst = static_cast<unsigned char*>(ctx->stage[b]) + static_cast<size_t>(t) * nb * img_bytes;
-    ALS_CUDA(ctx, cudaMemcpyAsync(dst, src, static_cast<size_t>(nb) * img_bytes, cudaMemcpyHostToDevice, ctx->copy_stream));
+  if (nb == s.N) {
+    // the whole batch: [T, nb, P, C] is one dense range on both sides -> one copy instead of T
+    ALS_CUDA(ctx, cudaMemcpyAsync(ctx->stage[b], host, static_cast<size_t>(s.T) * nb * img_bytes, cudaMemcpyHostToDevice,
+                                  ctx->copy_stream));
+  } else {
+    for (int64_t t = 0; t < s.T; ++t) {
+      const unsigned char* src = host + (static_cast<size_t>(t) * s.N + n0) * img_bytes;
+      unsigned char* dst = static_cast<unsigned char*>(ctx->stage[b]) + static_cast<size_t>(t) * nb * img_bytes;
+      ALS_CUDA(ctx, cudaMemcpyAsync(dst, src, static_cast<size_t>(nb) * img_bytes, cudaMemcpyHostToDevice, ctx->copy_stream));
+    }
   }
   ALS_CUDA(ctx, cudaEventRecord(ctx->ev_copied[b], ctx->copy_stream));
   *buf_out = b;
@@ -350,8 +320,9 @@ int als_ctx_create(int device, als_ctx** out) {
     ok = cudaEventCreateWithFlags(&ctx->ev_copied[b], cudaEventDisableTiming) == cudaSuccess &&
          cudaEventCreateWithFlags(&ctx->ev_scored[b], cudaEventDisableTiming) == cudaSuccess;
   }
+  ok = ok && cudaEventCreateWithFlags(&ctx->ev_scratch, cudaEventDisableTiming) == cudaSuccess;
   ok = ok && cudaMalloc(reinterpret_cast<void**>(&ctx->tile_counter), 128) == cudaSuccess &&
-       cudaMemset(ctx->tile_counter, 0, 128) == cudaSuccess;
+       cudaMemset(ctx->tile_counter, 0, 128) == cudaSuccess && cudaDeviceSynchronize() == cudaSuccess;
   if (!ok) {
     (void)cudaGetLastError();
     als_ctx_destroy(ctx);
@@ -366,11 +337,16 @@ int als_ctx_destroy(als_ctx* ctx) {
   DeviceGuard g(ctx->device);
   if (ctx->stream) cudaStreamSynchronize(ctx->stream);
   if (ctx->copy_stream) cudaStreamSynchronize(ctx->copy_stream);
-  void* ptrs[] = {ctx->acc, ctx->flags, ctx->tile_counter, ctx->scores_dev, ctx->index_dev, ctx->pool32, ctx->sel_ids, ctx->sel_keys,
-                  ctx->sel_tmp_keys, ctx->sel_tmp_ids, ctx->sel_out_keys, ctx->sel_out_ids, ctx->stage[0], ctx->stage[1],
-                  ctx->maps_dev, ctx->flush_buf, ctx->head_weights};
+  if (ctx->scratch_used) cudaEventSynchronize(ctx->ev_scratch);
+  als_comm_destroy(ctx);
+  void* ptrs[] = {ctx->acc, ctx->flags, ctx->tile_counter, ctx->scores_dev, ctx->index_dev, ctx->pool32, ctx->sel_ids,
+                  ctx->sel_out, ctx->sel_tmp_keys, ctx->sel_tmp_ids, ctx->stage[0], ctx->stage[1], ctx->maps_dev,
+                  ctx->flush_buf, ctx->head_weights, ctx->mc_state, ctx->xchg_send, ctx->xchg_recv};
   for (void* p : ptrs)
     if (p) cudaFree(p);
+  if (ctx->sel_ids_host) cudaFreeHost(ctx->sel_ids_host);
+  if (ctx->sel_out_host) cudaFreeHost(ctx->sel_out_host);
+  if (ctx->ev_scratch) cudaEventDestroy(ctx->ev_scratch);
   for (int b = 0; b < 2; ++b) {
     if (ctx->ev_copied[b]) cudaEventDestroy(ctx->ev_copied[b]);
     if (ctx->ev_scored[b]) cudaEventDestroy(ctx->ev_scored[b]);
@@ -387,9 +363,17 @@ int64_t als_launch_count(const als_ctx* ctx) { return ctx ? ctx->launches : 0; }
 int als_ctx_set_stream(als_ctx* ctx, void* stream) {
   if (!ctx) return fail(nullptr, ALS_ERR_INVALID, "context is NULL");
   DeviceGuard g(ctx->device);
-  ALS_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
-  if (ctx->owns_stream && ctx->stream) ALS_CUDA(ctx, cudaStreamDestroy(ctx->stream));
-  ctx->stream = static_cast<cudaStream_t>(stream);
+  cudaStream_t next = static_cast<cudaStream_t>(stream);
+  if (next == ctx->stream && !ctx->owns_stream) return ALS_OK;
+  // order the new stream behind everything queued on the old one (pool vector, staging, selection scratch)
+  cudaEvent_t ev;
+  ALS_CUDA(ctx, cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
+  cudaError_t e = cudaEventRecord(ev, ctx->stream);
+  if (e == cudaSuccess) e = cudaStreamWaitEvent(next, ev, 0);
+  cudaEventDestroy(ev);
+  ALS_CUDA(ctx, e);
+  if (ctx->owns_stream && ctx->stream) ALS_CUDA(ctx, cudaStreamDestroy(ctx->stream));  // released once its work is done
+  ctx->stream = next;
   ctx->owns_stream = false;
   return ALS_OK;
 }
@@ -409,8 +393,8 @@ int als_score(als_ctx* ctx, const void* logits, int dtype, int64_t T, int64_t N,
     ALS_TRY(check_device_ptr(ctx, mask, "mask"));
   }
   ALS_TRY(ensure_acc(ctx, N));
-  cudaStream_t st = stream ? static_cast<cudaStream_t>(stream) : ctx->stream;
-  return score_device(ctx, logits, dtype, s, measure, scores, nullptr, nullptr, 0, conf_map, label, mask, threshold, st);
+  return score_device(ctx, logits, dtype, s, measure, scores, nullptr, nullptr, 0, conf_map, label, mask, threshold,
+                      resolve_stream(ctx, stream));
 }
 
 int als_score_host(als_ctx* ctx, const void* logits, int dtype, int64_t T, int64_t N, int64_t H, int64_t W, int64_t C,
@@ -462,7 +446,7 @@ int als_score_host(als_ctx* ctx, const void* logits, int dtype, int64_t T, int64
   return ALS_OK;
 }
 
-int als_score_dlpack(als_ctx* ctx, void* managed, int measure, double* scores) {
+int als_score_dlpack(als_ctx* ctx, void* managed, int measure, double* scores, void* stream) {
   if (!ctx) return fail(nullptr, ALS_ERR_INVALID, "context is NULL");
   if (!managed) return fail(ctx, ALS_ERR_INVALID, "DLManagedTensor is NULL");
   const AlsDLTensor& t = static_cast<AlsDLManagedTensor*>(managed)->dl_tensor;
@@ -496,14 +480,17 @@ int als_score_dlpack(als_ctx* ctx, void* managed, int measure, double* scores) {
       if (s.N == 0) return ALS_OK;
       DeviceGuard g(ctx->device);
       ALS_TRY(ensure_acc(ctx, s.N));
-      ALS_TRY(grow(ctx, &ctx->scores_dev, &ctx->scores_cap, s.N, false));
-      // The producer's work may still be in flight on its own stream: order behind everything on the device.
-      ALS_CUDA(ctx, cudaDeviceSynchronize());
-      ALS_TRY(score_device(ctx, data, dtype, s, measure, ctx->scores_dev, nullptr, nullptr, 0, nullptr, nullptr, nullptr,
-                           0.f, ctx->stream));
-      ALS_CUDA(ctx, cudaMemcpyAsync(scores, ctx->scores_dev, static_cast<size_t>(s.N) * sizeof(double),
-                                    cudaMemcpyDeviceToHost, ctx->stream));
+      // scores_dev belongs to the context's stream: nothing of it may still be in flight when `st` writes it
       ALS_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+      ALS_TRY(grow(ctx, &ctx->scores_dev, &ctx->scores_cap, s.N, false));
+      // DLPack stream exchange: the producer made the tensor ready on `stream` (the stream handed to its
+      // __dlpack__(stream=...)), so enqueueing there is all the ordering that is needed.
+      cudaStream_t st = resolve_stream(ctx, stream);
+      ALS_TRY(score_device(ctx, data, dtype, s, measure, ctx->scores_dev, nullptr, nullptr, 0, nullptr, nullptr, nullptr,
+                           0.f, st));
+      ALS_CUDA(ctx, cudaMemcpyAsync(scores, ctx->scores_dev, static_cast<size_t>(s.N) * sizeof(double),
+                                    cudaMemcpyDeviceToHost, st));
+      ALS_CUDA(ctx, cudaStreamSynchronize(st));
       return ALS_OK;
     }
     case kAlsDLCPU:
@@ -587,12 +574,13 @@ int score_features_device(als_ctx* ctx, const void* features, int64_t T, int64_t
   p.n_rowblocks = static_cast<int>((h + p.rows_per_unit - 1) / p.rows_per_unit);
   p.n_units = N * p.n_rowblocks * p.n_strips;
   p.g = als::head_geometry(C);
+  ALS_TRY(scratch_begin(ctx, stream));
   ALS_CUDA(ctx, als::launch_head(plan, p, stream));
   ALS_CUDA(ctx, als::launch_finalize(ctx->acc, ctx->acc_cap, ctx->flags, ctx->tile_counter, static_cast<int>(N),
                                      ldexp(1.0, -shift) / static_cast<double>(P), scores64, pool32, example_index_dev,
                                      num_examples, stream));
   ctx->launches += 2;
-  return ALS_OK;
+  return scratch_end(ctx, stream);
 }
 
 }  // namespace
@@ -661,8 +649,8 @@ int als_score_features(als_ctx* ctx, const void* features, int64_t T, int64_t N,
   ALS_TRY(check_device_ptr(ctx, label, "label"));
   ALS_TRY(check_device_ptr(ctx, mask, "mask"));
   ALS_TRY(ensure_acc(ctx, N));
-  cudaStream_t st = stream ? static_cast<cudaStream_t>(stream) : ctx->stream;
-  return score_features_device(ctx, features, T, N, h, w, measure, scores, nullptr, nullptr, 0, conf_map, label, mask, threshold, st);
+  return score_features_device(ctx, features, T, N, h, w, measure, scores, nullptr, nullptr, 0, conf_map, label, mask, threshold,
+                               resolve_stream(ctx, stream));
 }
 
 int als_pool_score_features_batch(als_ctx* ctx, const void* features, int features_on_host, int64_t T, int64_t B, int64_t h,
@@ -770,23 +758,105 @@ int als_pool_scores(als_ctx* ctx, float* out, int64_t num_examples) {
   return ALS_OK;
 }
 
-static int ensure_select(als_ctx* ctx, int64_t M) {
-  if (M <= ctx->sel_cap) return ALS_OK;
-  int64_t cap = ctx->sel_cap > 0 ? ctx->sel_cap : 4096;
-  while (cap < M) cap *= 2;
-  ALS_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
-  void** ptrs[] = {(void**)&ctx->sel_ids, (void**)&ctx->sel_keys, (void**)&ctx->sel_tmp_keys, (void**)&ctx->sel_tmp_ids,
-                   (void**)&ctx->sel_out_keys, (void**)&ctx->sel_out_ids};
-  const size_t sizes[] = {8, 4, 4, 8, 4, 8};
-  for (int i = 0; i < 6; ++i) {
-    if (*ptrs[i]) ALS_CUDA(ctx, cudaFree(*ptrs[i]));
-    *ptrs[i] = nullptr;
+}  // extern "C"
+
+namespace als {
+
+// :705  the ids must index the pool vector, and be unique (duplicates would make the k-smallest set ill-defined)
+int validate_unlabelled(als_ctx* ctx, const int64_t* unlabelled, int64_t M) {
+  std::vector<uint64_t> seen(static_cast<size_t>((ctx->pool_n + 63) / 64), 0);
+  for (int64_t i = 0; i < M; ++i) {
+    const int64_t id = unlabelled[i];
+    if (id < 0 || id >= ctx->pool_n)
+      return fail(ctx, ALS_ERR_INVALID, "unlabelled[%lld]=%lld out of range [0, %lld)", (long long)i, (long long)id,
+                  (long long)ctx->pool_n);
+    uint64_t& w = seen[static_cast<size_t>(id >> 6)];
+    const uint64_t bit = 1ull << (id & 63);
+    if (w & bit) return fail(ctx, ALS_ERR_INVALID, "unlabelled[%lld]=%lld appears twice (ids must be unique)", (long long)i, (long long)id);
+    w |= bit;
   }
-  ctx->sel_cap = 0;
-  for (int i = 0; i < 6; ++i) ALS_CUDA(ctx, cudaMalloc(ptrs[i], static_cast<size_t>(cap) * sizes[i]));
-  ctx->sel_cap = cap;
   return ALS_OK;
 }
+
+// unlabelled (host) -> pinned mirror -> ctx->sel_ids on the context's stream
+int upload_unlabelled(als_ctx* ctx, const int64_t* unlabelled, int64_t M) {
+  ALS_TRY(grow(ctx, &ctx->sel_ids, &ctx->sel_ids_cap, M, false));
+  size_t cap = static_cast<size_t>(ctx->sel_ids_host_cap) * 8;
+  void* hp = ctx->sel_ids_host;
+  ALS_TRY(grow_pinned(ctx, &hp, &cap, static_cast<size_t>(M) * 8));
+  ctx->sel_ids_host = static_cast<long long*>(hp);
+  ctx->sel_ids_host_cap = static_cast<int64_t>(cap / 8);
+  // the previous selection's copy out of this pinned buffer completed before that call returned (it synchronises)
+  memcpy(ctx->sel_ids_host, unlabelled, static_cast<size_t>(M) * 8);
+  ALS_CUDA(ctx, cudaMemcpyAsync(ctx->sel_ids, ctx->sel_ids_host, static_cast<size_t>(M) * 8, cudaMemcpyHostToDevice, ctx->stream));
+  return ALS_OK;
+}
+
+// Result block of a selection, device and pinned host mirror: {count, status} | ids[k] | keys[k] | uconf[M]
+SelectBlock select_block(int64_t k, int64_t M) {
+  SelectBlock b;
+  b.off_ids = 16;
+  b.off_keys = b.off_ids + static_cast<size_t>(k) * 8;
+  b.off_uconf = (b.off_keys + static_cast<size_t>(k) * 4 + 15) & ~static_cast<size_t>(15);
+  b.bytes = b.off_uconf + static_cast<size_t>(M) * 4;
+  return b;
+}
+
+int ensure_select_block(als_ctx* ctx, const SelectBlock& b, int64_t kmax) {
+  void* p = ctx->sel_out;
+  ALS_TRY(grow_bytes(ctx, &p, &ctx->sel_out_cap, b.bytes));
+  ctx->sel_out = static_cast<unsigned char*>(p);
+  p = ctx->sel_out_host;
+  ALS_TRY(grow_pinned(ctx, &p, &ctx->sel_out_host_cap, b.bytes));
+  ctx->sel_out_host = static_cast<unsigned char*>(p);
+  if (kmax > kSelFusedMaxK && kmax > ctx->sel_tmp_cap) {
+    ALS_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    if (ctx->sel_tmp_keys) ALS_CUDA(ctx, cudaFree(ctx->sel_tmp_keys));
+    if (ctx->sel_tmp_ids) ALS_CUDA(ctx, cudaFree(ctx->sel_tmp_ids));
+    ctx->sel_tmp_keys = nullptr;
+    ctx->sel_tmp_ids = nullptr;
+    ctx->sel_tmp_cap = 0;
+    int64_t cap = 4096;
+    while (cap < kmax) cap *= 2;
+    ALS_CUDA(ctx, cudaMalloc(reinterpret_cast<void**>(&ctx->sel_tmp_keys), static_cast<size_t>(cap) * 4));
+    ALS_CUDA(ctx, cudaMalloc(reinterpret_cast<void**>(&ctx->sel_tmp_ids), static_cast<size_t>(cap) * 8));
+    ctx->sel_tmp_cap = cap;
+  }
+  return ALS_OK;
+}
+
+SelectOut select_out_of(als_ctx* ctx, const SelectBlock& b, int64_t M) {
+  SelectOut o{};
+  o.count = reinterpret_cast<long long*>(ctx->sel_out);
+  o.ids = reinterpret_cast<long long*>(ctx->sel_out + b.off_ids);
+  o.keys = reinterpret_cast<float*>(ctx->sel_out + b.off_keys);
+  o.pad_base = -1;
+  o.uconf = reinterpret_cast<float*>(ctx->sel_out + b.off_uconf);
+  o.uconf_ids = ctx->sel_ids;
+  o.uconf_M = M;
+  o.uconf_pool = ctx->pool32;
+  return o;
+}
+
+// ONE device->host copy of the whole block, then unpack into the caller's arrays.
+int fetch_select_block(als_ctx* ctx, const SelectBlock& b, int64_t k, int64_t M, int64_t* out_ids, float* out_unlabelled_conf,
+                       int64_t* out_count) {
+  ALS_CUDA(ctx, cudaMemcpyAsync(ctx->sel_out_host, ctx->sel_out, b.bytes, cudaMemcpyDeviceToHost, ctx->stream));
+  ALS_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+  const long long* hdr = reinterpret_cast<const long long*>(ctx->sel_out_host);
+  if (hdr[1] != 0)
+    return fail(ctx, ALS_ERR_INVALID, "the ranks' shards [shard_lo, shard_hi) do not tile [0, %lld): every example needs exactly one owner",
+                (long long)ctx->pool_n);
+  const int64_t n = hdr[0] < k ? hdr[0] : k;
+  if (n > 0) memcpy(out_ids, ctx->sel_out_host + b.off_ids, static_cast<size_t>(n) * 8);
+  if (out_unlabelled_conf && M > 0) memcpy(out_unlabelled_conf, ctx->sel_out_host + b.off_uconf, static_cast<size_t>(M) * 4);
+  *out_count = n;
+  return ALS_OK;
+}
+
+}  // namespace als
+
+extern "C" {
 
 int als_pool_select(als_ctx* ctx, const int64_t* unlabelled, int64_t M, int64_t selection_size, int64_t* out_ids,
                     float* out_unlabelled_conf, int64_t* out_count) {
@@ -797,32 +867,27 @@ int als_pool_select(als_ctx* ctx, const int64_t* unlabelled, int64_t M, int64_t 
   *out_count = 0;
   if (M == 0) return ALS_OK;
   if (!unlabelled) return fail(ctx, ALS_ERR_INVALID, "unlabelled is NULL");
-  for (int64_t i = 0; i < M; ++i)
-    if (unlabelled[i] < 0 || unlabelled[i] >= ctx->pool_n)
-      return fail(ctx, ALS_ERR_INVALID, "unlabelled[%lld]=%lld out of range [0, %lld)", (long long)i,
-                  (long long)unlabelled[i], (long long)ctx->pool_n);
+  ALS_TRY(als::validate_unlabelled(ctx, unlabelled, M));
   // :707-708  selection_size = min(len(unlabelled), selection_size); negative sizes never reach here (:779)
-  int64_t k = selection_size < 0 ? 0 : (selection_size < M ? selection_size : M);
+  const int64_t k = selection_size < 0 ? 0 : (selection_size < M ? selection_size : M);
   if (k > 0 && !out_ids) return fail(ctx, ALS_ERR_INVALID, "out_ids is NULL");
   DeviceGuard g(ctx->device);
-  ALS_TRY(ensure_select(ctx, M));
-  ALS_CUDA(ctx, cudaMemcpyAsync(ctx->sel_ids, unlabelled, static_cast<size_t>(M) * sizeof(int64_t), cudaMemcpyHostToDevice,
-                                ctx->stream));
-  ALS_CUDA(ctx, als::launch_gather(ctx->pool32, ctx->sel_ids, M, ctx->sel_keys, ctx->stream));
-  ctx->launches += 1;
-  if (k > 0) {
-    ALS_CUDA(ctx, als::launch_select(ctx->sel_keys, ctx->sel_ids, M, k, ctx->sel_tmp_keys, ctx->sel_tmp_ids,
-                                     ctx->sel_out_keys, ctx->sel_out_ids, ctx->stream));
-    ctx->launches += 2;
-    ALS_CUDA(ctx, cudaMemcpyAsync(out_ids, ctx->sel_out_ids, static_cast<size_t>(k) * sizeof(int64_t),
-                                  cudaMemcpyDeviceToHost, ctx->stream));
-  }
-  if (out_unlabelled_conf)
-    ALS_CUDA(ctx, cudaMemcpyAsync(out_unlabelled_conf, ctx->sel_keys, static_cast<size_t>(M) * sizeof(float),
-                                  cudaMemcpyDeviceToHost, ctx->stream));
-  ALS_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
-  *out_count = k;
-  return ALS_OK;
+  const als::SelectBlock blk = als::select_block(k, M);
+  ALS_TRY(als::ensure_select_block(ctx, blk, k));
+  ALS_TRY(als::upload_unlabelled(ctx, unlabelled, M));
+  // one launch: gather confidence[unlabelled] (:705), radix-select the k lowest (:710-712), order them, pack
+  als::SelectSrc src{};
+  src.mode = 1;
+  src.ids = ctx->sel_ids;
+  src.pool = ctx->pool32;
+  src.lo = INT64_MIN;
+  src.hi = INT64_MAX;
+  const als::SelectOut out = als::select_out_of(ctx, blk, M);
+  int nl = 0;
+  ALS_CUDA(ctx, als::launch_select(src, M, k, als::ScatterDesc{}, als::ExportDesc{}, out, ctx->sel_tmp_keys, ctx->sel_tmp_ids,
+                                   ctx->stream, &nl));
+  ctx->launches += nl;
+  return als::fetch_select_block(ctx, blk, k, M, out_ids, out_unlabelled_conf, out_count);
 }
 
 int als_select_smallest(als_ctx* ctx, const float* keys, const int64_t* ids, int64_t M, int64_t k, float* out_keys,
@@ -837,12 +902,23 @@ int als_select_smallest(als_ctx* ctx, const float* keys, const int64_t* ids, int
   ALS_TRY(check_device_ptr(ctx, ids, "ids"));
   ALS_TRY(check_device_ptr(ctx, out_keys, "out_keys"));
   ALS_TRY(check_device_ptr(ctx, out_ids, "out_ids"));
-  ALS_TRY(ensure_select(ctx, kk));
-  cudaStream_t st = stream ? static_cast<cudaStream_t>(stream) : ctx->stream;
-  ALS_CUDA(ctx, als::launch_select(keys, reinterpret_cast<const long long*>(ids), M, kk, ctx->sel_tmp_keys,
-                                   ctx->sel_tmp_ids, out_keys, reinterpret_cast<long long*>(out_ids), st));
-  ctx->launches += 2;
-  return ALS_OK;
+  const als::SelectBlock blk = als::select_block(0, 0);  // only the {count, status} header is used
+  ALS_TRY(als::ensure_select_block(ctx, blk, kk));
+  cudaStream_t st = resolve_stream(ctx, stream);
+  ALS_TRY(scratch_begin(ctx, st));  // the header words and the large-k scratch are per context
+  als::SelectSrc src{};
+  src.mode = 0;
+  src.keys = keys;
+  src.ids = reinterpret_cast<const long long*>(ids);
+  als::SelectOut out{};
+  out.count = reinterpret_cast<long long*>(ctx->sel_out);
+  out.keys = out_keys;
+  out.ids = reinterpret_cast<long long*>(out_ids);
+  out.pad_base = -1;
+  int nl = 0;
+  ALS_CUDA(ctx, als::launch_select(src, M, kk, als::ScatterDesc{}, als::ExportDesc{}, out, ctx->sel_tmp_keys, ctx->sel_tmp_ids, st, &nl));
+  ctx->launches += nl;
+  return scratch_end(ctx, st);
 }
 
 // ---- synthetic pool / bench helpers ----------------------------------------------------------------
@@ -857,7 +933,7 @@ int als_synth_logits(als_ctx* ctx, void* out, int dtype, int64_t T, int64_t n0, 
   DeviceGuard g(ctx->device);
   ALS_TRY(check_device_ptr(ctx, out, "out"));
   if (!out) return fail(ctx, ALS_ERR_INVALID, "out is NULL");
-  cudaStream_t st = stream ? static_cast<cudaStream_t>(stream) : ctx->stream;
+  cudaStream_t st = resolve_stream(ctx, stream);
   ALS_CUDA(ctx, als::launch_synth(out, dtype, T, n0, n_imgs, H * W, static_cast<int>(C), seed, mc, st));
   ctx->launches += 1;
   return ALS_OK;
@@ -870,7 +946,7 @@ int als_flush_l2(als_ctx* ctx, void* stream) {
     ctx->flush_bytes = 512ull << 20;
     ALS_CUDA(ctx, cudaMalloc(&ctx->flush_buf, ctx->flush_bytes));
   }
-  cudaStream_t st = stream ? static_cast<cudaStream_t>(stream) : ctx->stream;
+  cudaStream_t st = resolve_stream(ctx, stream);
   ALS_CUDA(ctx, als::launch_fill(ctx->flush_buf, ctx->flush_bytes, st));
   return ALS_OK;
 }
@@ -892,6 +968,154 @@ int als_describe_launch(als_ctx* ctx, int dtype, int64_t T, int64_t N, int64_t H
   if (stages) *stages = plan.stages;
   if (tile_pixels) *tile_pixels = plan.tile_pixels;
   return ALS_OK;
+}
+
+int als_describe_head_launch(als_ctx* ctx, int64_t T, int measure, char* name, int* grid, int* block, int* smem_bytes) {
+  if (!ctx) return fail(nullptr, ALS_ERR_INVALID, "context is NULL");
+  if (ctx->head_C <= 0) return fail(ctx, ALS_ERR_STATE, "als_head_prepare has not been called");
+  const als::HeadPlan plan = als::plan_head(static_cast<int>(ctx->head_C), measure, static_cast<int>(T), ctx->num_sms);
+  if (!plan.func) return fail(ctx, ALS_ERR_UNSUPPORTED, "no fused-head kernel for C=%lld, T=%lld", (long long)ctx->head_C, (long long)T);
+  if (name) snprintf(name, 128, "%s C=%lld: tcgen05 split-TF32 UMMA 128xNx8 + TMEM epilogue", plan.name, (long long)ctx->head_C);
+  if (grid) *grid = plan.grid;
+  if (block) *block = plan.block;
+  if (smem_bytes) *smem_bytes = plan.smem_bytes;
+  return ALS_OK;
+}
+
+// ---- streamed Monte-Carlo accumulation ---------------------------------------------------------------
+
+int als_mc_begin(als_ctx* ctx, int dtype, int64_t N, int64_t H, int64_t W, int64_t C, uint8_t* label) {
+  const Shape s{1, N, H, W, C};
+  ALS_TRY(check_common(ctx, reinterpret_cast<const void*>(16), dtype, s, ALS_ENTROPY, label != nullptr));
+  DeviceGuard g(ctx->device);
+  ALS_TRY(check_device_ptr(ctx, label, "label"));
+  ctx->mc_samples = -1;
+  const als::McPlan plan = als::plan_mc(dtype, static_cast<int>(C), N * s.P(), true, ctx->num_sms, ctx->max_smem);
+  const als::McPlan generic = als::plan_mc(dtype, static_cast<int>(C), N * s.P(), false, ctx->num_sms, ctx->max_smem);
+  const long long need = plan.state_floats > generic.state_floats ? plan.state_floats : generic.state_floats;
+  if (static_cast<size_t>(need) > ctx->mc_state_cap) {
+    ALS_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    if (ctx->mc_state) ALS_CUDA(ctx, cudaFree(ctx->mc_state));
+    ctx->mc_state = nullptr;
+    ctx->mc_state_cap = 0;
+    ALS_CUDA(ctx, cudaMalloc(reinterpret_cast<void**>(&ctx->mc_state), static_cast<size_t>(need) * sizeof(float)));
+    ctx->mc_state_cap = static_cast<size_t>(need);
+  }
+  ALS_TRY(ensure_acc(ctx, N));
+  ctx->mc_dtype = dtype;
+  ctx->mc_N = N;
+  ctx->mc_H = H;
+  ctx->mc_W = W;
+  ctx->mc_C = C;
+  ctx->mc_label = label;
+  ctx->mc_samples = 0;
+  ctx->mc_tiled = -1;
+  return ALS_OK;
+}
+
+int als_mc_add_sample(als_ctx* ctx, const void* logits, int logits_on_host) {
+  if (!ctx) return fail(nullptr, ALS_ERR_INVALID, "context is NULL");
+  if (ctx->mc_samples < 0) return fail(ctx, ALS_ERR_STATE, "als_mc_begin has not been called");
+  if (ctx->mc_N == 0) { ++ctx->mc_samples; return ALS_OK; }
+  if (!logits) return fail(ctx, ALS_ERR_INVALID, "logits pointer is NULL");
+  if (ctx->mc_samples >= (1 << 24)) return fail(ctx, ALS_ERR_INVALID, "too many samples");
+  DeviceGuard g(ctx->device);
+  const Shape s{1, ctx->mc_N, ctx->mc_H, ctx->mc_W, ctx->mc_C};
+  const int es = ctx->mc_dtype == ALS_F32 ? 4 : 2;
+  const void* dev = logits;
+  int b = -1;
+  if (logits_on_host) {
+    ALS_TRY(ensure_stage(ctx, static_cast<size_t>(s.elems()) * es));
+    ALS_TRY(stage_chunk(ctx, static_cast<const unsigned char*>(logits), s, es, 0, s.N, &b));
+    ALS_CUDA(ctx, cudaStreamWaitEvent(ctx->stream, ctx->ev_copied[b], 0));
+    dev = ctx->stage[b];
+  } else {
+    ALS_TRY(check_device_ptr(ctx, logits, "logits"));
+  }
+  // one layout for the whole accumulation: a misaligned sample forces the generic kernels from the first sample on
+  const bool aligned = reinterpret_cast<uintptr_t>(dev) % 16 == 0;
+  const als::McPlan plan = als::plan_mc(ctx->mc_dtype, static_cast<int>(s.C), s.N * s.P(), aligned && ctx->mc_tiled != 0,
+                                        ctx->num_sms, ctx->max_smem);
+  if (ctx->mc_tiled < 0) ctx->mc_tiled = plan.tiled ? 1 : 0;
+  else if ((ctx->mc_tiled == 1) != plan.tiled)
+    return fail(ctx, ALS_ERR_INVALID, "samples of one accumulation must all be 16-byte aligned (or none of them)");
+  als::ScoreParams p{};
+  p.logits = dev;
+  p.total_pixels = s.N * s.P();
+  p.P = s.P();
+  p.T = 1;
+  p.C = static_cast<int>(s.C);
+  p.tile_counter = ctx->tile_counter;
+  p.acc = ctx->acc;
+  p.acc_stride = ctx->acc_cap;
+  p.flags = ctx->flags;
+  p.label = ctx->mc_samples == 0 ? ctx->mc_label : nullptr;
+  ALS_TRY(scratch_begin(ctx, ctx->stream));
+  ALS_CUDA(ctx, als::launch_mc_update(plan, ctx->mc_dtype, p, ctx->mc_state, static_cast<int>(ctx->mc_samples), ctx->stream));
+  ctx->launches += 1;
+  ALS_TRY(scratch_end(ctx, ctx->stream));
+  if (b >= 0) {
+    ALS_CUDA(ctx, cudaEventRecord(ctx->ev_scored[b], ctx->stream));
+    ALS_CUDA(ctx, cudaEventSynchronize(ctx->ev_copied[b]));  // "returns once staged"
+  }
+  ++ctx->mc_samples;
+  return ALS_OK;
+}
+
+int als_mc_finish(als_ctx* ctx, int measure, double* scores, const int64_t* example_index, float* conf_map, uint8_t* mask,
+                  float threshold) {
+  if (!ctx) return fail(nullptr, ALS_ERR_INVALID, "context is NULL");
+  if (ctx->mc_samples < 0) return fail(ctx, ALS_ERR_STATE, "als_mc_begin has not been called");
+  if (measure < ALS_ENTROPY || measure > ALS_VARIANCE) return fail(ctx, ALS_ERR_UNSUPPORTED, "Uncertainty function not implemented.");
+  const int64_t T = ctx->mc_samples;
+  if (T < 1) return fail(ctx, ALS_ERR_STATE, "no sample has been added");
+  if (measure == ALS_VARIANCE && T < 2) return fail(ctx, ALS_ERR_INVALID, "measure 'variance' needs T >= 2 Monte-Carlo samples");
+  const Shape s{1, ctx->mc_N, ctx->mc_H, ctx->mc_W, ctx->mc_C};
+  ctx->mc_samples = -1;
+  if (s.N == 0) return ALS_OK;
+  if (example_index && ctx->pool_n < 0) return fail(ctx, ALS_ERR_STATE, "als_pool_begin has not been called");
+  if (example_index)
+    for (int64_t i = 0; i < s.N; ++i)
+      if (example_index[i] < 0 || example_index[i] >= ctx->pool_n)
+        return fail(ctx, ALS_ERR_INVALID, "example_index[%lld]=%lld out of range [0, %lld)", (long long)i,
+                    (long long)example_index[i], (long long)ctx->pool_n);
+  DeviceGuard g(ctx->device);
+  ALS_TRY(check_device_ptr(ctx, scores, "scores"));
+  ALS_TRY(check_device_ptr(ctx, conf_map, "conf_map"));
+  ALS_TRY(check_device_ptr(ctx, mask, "mask"));
+  if (example_index) {
+    ALS_TRY(grow(ctx, &ctx->index_dev, &ctx->index_cap, s.N, false));
+    ALS_CUDA(ctx, cudaMemcpyAsync(ctx->index_dev, example_index, static_cast<size_t>(s.N) * sizeof(int64_t), cudaMemcpyHostToDevice,
+                                  ctx->stream));
+  }
+  const als::McPlan plan = als::plan_mc(ctx->mc_dtype, static_cast<int>(s.C), s.N * s.P(), ctx->mc_tiled == 1, ctx->num_sms,
+                                        ctx->max_smem);
+  const long long P = s.P();
+  int shift = 62 - ceil_log2_ll(P);
+  if (shift > 44) shift = 44;
+  als::ScoreParams p{};
+  p.total_pixels = s.N * P;
+  p.P = P;
+  p.T = static_cast<int>(T);
+  p.C = static_cast<int>(s.C);
+  p.measure = measure;
+  p.inv_log2_c = static_cast<float>(1.0 / log2(static_cast<double>(s.C)));
+  p.threshold = threshold;
+  p.inv_T = 1.0f / static_cast<float>(T);
+  p.fx_scale = ldexpf(1.0f, shift);
+  p.acc = ctx->acc;
+  p.acc_stride = ctx->acc_cap;
+  p.flags = ctx->flags;
+  p.tile_counter = ctx->tile_counter;
+  p.conf_map = conf_map;
+  p.mask = mask;
+  ALS_TRY(scratch_begin(ctx, ctx->stream));
+  ALS_CUDA(ctx, als::launch_mc_finish(plan, ctx->mc_dtype, p, ctx->mc_state, ctx->stream));
+  ALS_CUDA(ctx, als::launch_finalize(ctx->acc, ctx->acc_cap, ctx->flags, ctx->tile_counter, static_cast<int>(s.N),
+                                     ldexp(1.0, -shift) / static_cast<double>(P), scores, example_index ? ctx->pool32 : nullptr,
+                                     example_index ? ctx->index_dev : nullptr, example_index ? ctx->pool_n : 0, ctx->stream));
+  ctx->launches += 2;
+  return scratch_end(ctx, ctx->stream);
 }
 
 }  // extern "C"

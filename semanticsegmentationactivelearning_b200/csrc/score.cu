@@ -22,125 +22,9 @@
 
 #include "common.cuh"
 #include "pixel_math.cuh"
+#include "tiles.cuh"
 
 namespace als {
-
-constexpr int kSmemHeader = 128 + 256;  // mbarriers (2 x 8 x 8 B) + per-stage TileMeta (8 x 32 B)
-static_assert(kSmemHeader % 128 == 0 && kMaxStages * 32 <= 256, "stage buffers must stay 128-byte aligned");
-
-// ---- compile-time launch policy -------------------------------------------------------
-__host__ __device__ constexpr int lpp_for(int C) { return C <= 36 ? 1 : C <= 72 ? 2 : C <= 144 ? 4 : 8; }
-__host__ __device__ constexpr int cdiv(int a, int b) { return (a + b - 1) / b; }
-__host__ __device__ constexpr int ppt_for(int C, int es, bool multi) {
-  const int lpp = lpp_for(C);
-  const int cl = cdiv(C, lpp);
-  const int row = (kConsumerThreads / lpp) * C * es;  // bytes per pixel-slot row
-  int ppt = 1;
-  const int reg_cap = multi ? 20 : 40;
-  while (ppt < 4 && 2 * ppt * cl <= reg_cap && 2 * ppt * row <= 32 * 1024) ppt *= 2;
-  return ppt;
-}
-__host__ __device__ constexpr int pow2_divisor(int v, int cap) {
-  int p = 1;
-  while (p < cap && v % (2 * p) == 0) p *= 2;
-  return p;
-}
-__host__ __device__ constexpr int gcd_i(int a, int b) { return b == 0 ? a : gcd_i(b, a % b); }
-
-template <typename E, int C, bool MULTI>
-struct Cfg {
-  static constexpr int ES = sizeof(E);
-  static constexpr int LPP = lpp_for(C);
-  static constexpr int CL = cdiv(C, LPP);
-  static constexpr bool EXACT = (LPP * CL == C);
-  static constexpr int G = kConsumerThreads / LPP;  // pixels per slot row
-  static constexpr int PPT = ppt_for(C, ES, MULTI);
-  static constexpr int TILE_PIX = G * PPT;
-  static constexpr int STAGE_BYTES = ((TILE_PIX * C * ES + 127) / 128) * 128;
-  // widest shared-memory access every lane's run start is aligned to
-  static constexpr int VB = EXACT ? pow2_divisor(gcd_i(CL * ES, C * ES), 16) : ES;
-  // resident CTAs per SM the kernel is compiled for: 3 when the per-thread class registers are few
-  // (more warps hide the dependent MUFU/FMA chains), else 2
-  static constexpr int MINB = (PPT * CL <= 24) ? 3 : 2;
-  static_assert((LPP - 1) * CL < C, "every lane must own at least one class");
-};
-
-// ---- shared memory -> registers -------------------------------------------------------
-template <typename E, int CL, int VB>
-__device__ __forceinline__ void load_run(const unsigned char* __restrict__ src, float (&x)[CL]) {
-  if constexpr (sizeof(E) == 4) {
-    if constexpr (VB == 16) {
-#pragma unroll
-      for (int i = 0; i < CL / 4; ++i) {
-        const float4 v = *reinterpret_cast<const float4*>(src + 16 * i);
-        x[4 * i] = v.x; x[4 * i + 1] = v.y; x[4 * i + 2] = v.z; x[4 * i + 3] = v.w;
-      }
-    } else if constexpr (VB == 8) {
-#pragma unroll
-      for (int i = 0; i < CL / 2; ++i) {
-        const float2 v = *reinterpret_cast<const float2*>(src + 8 * i);
-        x[2 * i] = v.x; x[2 * i + 1] = v.y;
-      }
-    } else {
-#pragma unroll
-      for (int j = 0; j < CL; ++j) x[j] = *reinterpret_cast<const float*>(src + 4 * j);
-    }
-  } else {  // bf16: value = bits << 16
-    if constexpr (VB == 16) {
-#pragma unroll
-      for (int i = 0; i < CL / 8; ++i) {
-        const uint4 v = *reinterpret_cast<const uint4*>(src + 16 * i);
-        const uint32_t w[4] = {v.x, v.y, v.z, v.w};
-#pragma unroll
-        for (int q = 0; q < 4; ++q) {
-          x[8 * i + 2 * q] = __uint_as_float(w[q] << 16);
-          x[8 * i + 2 * q + 1] = __uint_as_float(w[q] & 0xffff0000u);
-        }
-      }
-    } else if constexpr (VB == 8) {
-#pragma unroll
-      for (int i = 0; i < CL / 4; ++i) {
-        const uint2 v = *reinterpret_cast<const uint2*>(src + 8 * i);
-        x[4 * i] = __uint_as_float(v.x << 16); x[4 * i + 1] = __uint_as_float(v.x & 0xffff0000u);
-        x[4 * i + 2] = __uint_as_float(v.y << 16); x[4 * i + 3] = __uint_as_float(v.y & 0xffff0000u);
-      }
-    } else if constexpr (VB == 4) {
-#pragma unroll
-      for (int i = 0; i < CL / 2; ++i) {
-        const uint32_t w = *reinterpret_cast<const uint32_t*>(src + 4 * i);
-        x[2 * i] = __uint_as_float(w << 16); x[2 * i + 1] = __uint_as_float(w & 0xffff0000u);
-      }
-    } else {
-#pragma unroll
-      for (int j = 0; j < CL; ++j)
-        x[j] = __uint_as_float(static_cast<uint32_t>(*reinterpret_cast<const uint16_t*>(src + 2 * j)) << 16);
-    }
-  }
-}
-
-// Lanes whose class run is only partly inside [0, C) (C not a multiple of LPP).
-template <typename E, int CL>
-__device__ __forceinline__ void load_run_partial(const unsigned char* __restrict__ src, float (&x)[CL], int nvalid) {
-#pragma unroll
-  for (int j = 0; j < CL; ++j) {
-    float v = -INFINITY;
-    if (j < nvalid) {
-      if constexpr (sizeof(E) == 4) v = *reinterpret_cast<const float*>(src + 4 * j);
-      else v = __uint_as_float(static_cast<uint32_t>(*reinterpret_cast<const uint16_t*>(src + 2 * j)) << 16);
-    }
-    x[j] = v;
-  }
-}
-
-// ---- the tiled kernel ------------------------------------------------------------------------
-// Per-stage tile descriptor the producer publishes next to the data (sample 0 of a tile only).
-struct TileMeta {
-  long long pix0;  // first global pixel of the tile, -1 = no more work
-  long long img;   // image of that pixel
-  long long off;   // its offset inside the image
-  int npix;        // pixels in the tile (< TILE_PIX only for the last tile of the pool)
-  int in_img;      // how many of them belong to `img` (the rest start the next image(s))
-};
 
 template <typename E, int C, int MEASURE>
 __global__ void __launch_bounds__(kBlockThreads, Cfg<E, C, (MEASURE == kMulti)>::MINB) score_tiles_kernel(const ScoreParams p) {
@@ -172,55 +56,8 @@ __global__ void __launch_bounds__(kBlockThreads, Cfg<E, C, (MEASURE == kMulti)>:
   const int lane = threadIdx.x & 31;
 
   if (warp == kConsumerThreads / 32) {
-    // ===== producer: one lane claims tiles and feeds the ring with 1-D bulk copies =====
-    // Tiles are claimed dynamically (first one static, the rest from a global counter) so SMs that
-    // see less HBM bandwidth simply take fewer tiles; the integer per-image sums make the result
-    // independent of who scored what.
-    if (lane == 0) {
-      const uint64_t policy = l2_policy_evict_first();
-      const E* base = static_cast<const E*>(p.logits);
-      int s = 0;
-      uint32_t ph = 0;
-      long long tile = blockIdx.x;
-      while (true) {
-        const bool live = tile < p.num_tiles;
-        // claim the next tile now; its latency hides behind this tile's copies
-        const long long next = live ? static_cast<long long>(gridDim.x) +
-                                          static_cast<long long>(atomicAdd(p.tile_counter, 1ull))
-                                    : tile;
-        if (!live) {
-          mbar_wait(&empty[s], ph ^ 1u);
-          meta[s].pix0 = -1;
-          mbar_arrive_expect_tx(&full[s], 0);
-          break;
-        }
-        const long long pix0 = tile * K::TILE_PIX;
-        const long long rem = p.total_pixels - pix0;
-        const uint32_t npix = rem < K::TILE_PIX ? static_cast<uint32_t>(rem) : K::TILE_PIX;
-        const uint32_t bytes = npix * C * ES;
-        const uint32_t bulk = bytes & ~15u;
-        const long long img = pix0 / p.P;
-        for (int t = 0; t < p.T; ++t) {
-          mbar_wait(&empty[s], ph ^ 1u);
-          unsigned char* dst = stage_base + static_cast<size_t>(s) * K::STAGE_BYTES;
-          const unsigned char* src = reinterpret_cast<const unsigned char*>(base + t * p.sample_stride + pix0 * C);
-          if (t == 0) {
-            const long long off = pix0 - img * p.P;
-            const long long left = p.P - off;  // pixels of image `img` from the tile start on
-            meta[s].pix0 = pix0;
-            meta[s].img = img;
-            meta[s].off = off;
-            meta[s].npix = static_cast<int>(npix);
-            meta[s].in_img = left < npix ? static_cast<int>(left) : static_cast<int>(npix);
-          }
-          for (uint32_t b = bulk; b < bytes; ++b) dst[b] = src[b];  // < 16 trailing bytes of the whole pool
-          mbar_arrive_expect_tx(&full[s], bulk);                    // release: publishes meta + tail bytes
-          if (bulk) bulk_g2s(dst, src, bulk, &full[s], policy);
-          if (++s == nstage) { s = 0; ph ^= 1u; }
-        }
-        tile = next;
-      }
-    }
+    // ===== producer: one lane claims tiles and feeds the ring with 1-D bulk copies (tiles.cuh) =====
+    if (lane == 0) produce_tiles<K, E, C>(p, full, empty, meta, stage_base, nstage);
     return;
   }
 
@@ -336,13 +173,6 @@ __global__ void __launch_bounds__(kBlockThreads, Cfg<E, C, (MEASURE == kMulti)>:
 }
 
 // ---- generic fallback: any C, any alignment (direct global loads, one thread per pixel) -----
-template <typename E>
-__device__ __forceinline__ float ld_elem(const E* p) {
-  if constexpr (sizeof(E) == 4) return *reinterpret_cast<const float*>(p);
-  else return __uint_as_float(static_cast<uint32_t>(*reinterpret_cast<const uint16_t*>(p)) << 16);
-}
-
-constexpr int kGenericThreads = 128;
 
 template <typename E>
 __global__ void __launch_bounds__(kGenericThreads) score_generic_kernel(const ScoreParams p) {
@@ -403,11 +233,11 @@ __global__ void __launch_bounds__(kGenericThreads) score_generic_kernel(const Sc
         const float r = rcp_approx(S);
         const float inv_t = __frcp_rn(static_cast<float>(t + 1));
         for (int c = 0; c < C; ++c) {
-          const float pj = ex2_approx((ld_elem(ps + c) - m1) * kLog2e) * r;
+          const float pj = __fmul_rn(ex2_approx((ld_elem(ps + c) - m1) * kLog2e), r);  // no contraction: streamed == resident
           float& m = mu_s[c * kGenericThreads + threadIdx.x];
-          const float delta = pj - m;
+          const float delta = __fsub_rn(pj, m);
           m = fmaf(delta, inv_t, m);
-          m2s = fmaf(delta, pj - m, m2s);
+          m2s = fmaf(delta, __fsub_rn(pj, m), m2s);
         }
       }
       if (p.measure == kVariance) {
@@ -479,10 +309,6 @@ cudaError_t launch_finalize(long long* acc, long long acc_stride, unsigned int* 
 }
 
 // ---- dispatch ------------------------------------------------------------------------------------
-// Class counts with a specialised tiled kernel; any other C runs the generic kernel.
-#define ALS_C_LIST(X) X(2) X(3) X(4) X(5) X(6) X(7) X(8) X(9) X(10) X(11) X(12) X(13) X(16) X(19) X(20) X(21) \
-  X(24) X(32) X(33) X(34) X(37) X(40) X(59) X(60) X(65) X(66) X(91) X(133) X(150) X(151) X(171) X(182)
-
 template <typename E, int C>
 static bool pick(int measure, int T, LaunchPlan& plan) {
   const bool multi = T > 1;

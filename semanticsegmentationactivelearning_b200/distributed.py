@@ -1,9 +1,18 @@
 """Pool sharded by image across GPUs: every rank scores its own images, only the per-rank
-top-k candidates and the small score vector cross NVLink (one all-gather each).
+top-k candidates and the small score vector cross NVLink (ONE all-gather).
 
 The reference runs the whole pool on GPU:0, eight images per sess.run
 (/root/reference/active_learning.py:689-700); images are independent, so the pool shards with
-no data-path collective.  One process per GPU (torchrun); NCCL on GPUs, gloo in CPU tests.
+no data-path collective.
+
+Two forms of the same exchange:
+
+* ``comm_init_torch`` + ``rank_confidence_sharded_device``: the product path.  The exchange lives behind the C ABI
+  (csrc/comm.cu: ``als_comm_init_rank`` / ``als_pool_select_global``): candidates are selected, all-gathered with
+  NCCL and merged on the device, one device->host copy.  torch.distributed is only used to hand the NCCL unique id
+  around.  (Single-process multi-GPU: ``Scorer.comm_init_all`` / ``Scorer.pool_select_global_all``.)
+* ``rank_confidence_sharded``: the same record exchange written against ``torch.distributed`` with host arrays, so
+  that the sharding / padding / merge logic is testable with gloo on machines without a GPU.
 """
 from __future__ import annotations
 
@@ -19,6 +28,23 @@ def shard_bounds(n: int, rank: int, world: int) -> Tuple[int, int]:
     base, extra = divmod(int(n), int(world))
     lo = rank * base + min(rank, extra)
     return lo, lo + base + (1 if rank < extra else 0)
+
+
+def comm_init_torch(scorer, group=None) -> None:
+    """Create the library's own NCCL communicator for ``scorer`` over the ranks of a torch.distributed group:
+    rank 0 draws the NCCL unique id, torch broadcasts the 128 bytes, every rank joins (collective)."""
+    import torch.distributed as dist
+    rank, world = dist.get_rank(group), dist.get_world_size(group)
+    box = [scorer.comm_unique_id() if rank == 0 else None]
+    dist.broadcast_object_list(box, src=dist.get_global_rank(group, 0) if group is not None else 0, group=group)
+    scorer.comm_init(rank, world, box[0])
+
+
+def rank_confidence_sharded_device(scorer, unlabelled, selection_size: int, shard: Tuple[int, int], max_shard: int = 0):
+    """:705-715 for a pool sharded by image, on the device (csrc/comm.cu).  ``scorer`` holds a full-size pool vector
+    (``pool_begin(num_examples)``) in which this rank has scored the example ids [shard[0], shard[1]); the shards of
+    all ranks tile [0, num_examples).  Returns (low_conf_examples, unlabelled_confidence), identical on all ranks."""
+    return scorer.pool_select_global(unlabelled, selection_size, shard, max_shard)
 
 
 def _device_select(scorer):

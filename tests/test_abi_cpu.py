@@ -25,7 +25,7 @@ def test_header_and_binding_agree(lib):
     assert declared == set(_lib.SIGNATURES), declared ^ set(_lib.SIGNATURES)
     for name in declared:
         assert hasattr(lib, name), name
-    assert lib.als_version() == 100
+    assert lib.als_version() == 110
 
 
 def test_header_cites_reference_lines():

@@ -73,7 +73,7 @@ def assert_ids(got_ids, want_scores32, unlabelled, k, what=""):
 def test_library_is_the_cuda_one():
     import semanticsegmentationactivelearning_b200 as A
     from semanticsegmentationactivelearning_b200 import _lib
-    assert _lib.load().als_version() == 100
+    assert _lib.load().als_version() == 110
     assert A.LIB_PATH.endswith("libalscore.so")
 
 
@@ -160,9 +160,98 @@ def test_input_validation(torch, scorer):
         scorer.score(torch.zeros(2, 4, 4, 38, device="cuda")[..., ::2], "entropy")     # strided
     with pytest.raises(ValueError):
         scorer.score(torch.zeros(2, 4, 4, 1, device="cuda"), "entropy")                 # one class
-    with pytest.raises(ValueError):
-        scorer.score(torch.zeros(2 * 4 * 4 * 19 + 1, device="cuda")[1:].view(2, 4, 4, 19), "entropy")  # misaligned
     assert scorer.score(torch.zeros(0, 4, 4, 19, device="cuda"), "entropy").numel() == 0
+
+
+def test_misaligned_and_odd_shapes(torch, scorer):
+    """No alignment requirement on the logits pointer (the reference accepts any shape): a device view that starts
+    4 bytes into an allocation, and batches of an odd-sized pool sliced by rank_confidence(batch_size=...), where
+    H*W*C*elemsize is not a multiple of 16, score like the aligned copy (the generic kernel takes over)."""
+    from oracle import reference_np as R, synth
+    from semanticsegmentationactivelearning_b200 import rank_confidence
+    x = synth.synth_logits(1, 0, 5, 7, 9, 19)
+    flat = torch.zeros(x.size + 1, device="cuda")
+    flat[1:] = torch.from_numpy(x).cuda().reshape(-1)
+    mis = flat[1:].view(5, 7, 9, 19)
+    assert mis.data_ptr() % 16 != 0
+    for measure in MEASURES:
+        want = R.score_pool(x, measure)
+        assert_scores(scorer.score(mis, measure), want, measure)
+        assert_scores(scorer.score(x, measure), want, measure)                     # host array (staged)
+    xt = synth.synth_logits(3, 0, 5, 7, 9, 19)
+    flat = torch.zeros(xt.size + 1, device="cuda")
+    flat[1:] = torch.from_numpy(xt).cuda().reshape(-1)
+    assert_scores(scorer.score(flat[1:].view(3, 5, 7, 9, 19), "variance"), R.score_pool(xt, "variance"))
+    # odd H*W, batch_size < N: every slice after the first starts at an address that is not a multiple of 16
+    unl = np.arange(5)
+    for src in (torch.from_numpy(x).cuda(), x, torch.from_numpy(x).cuda().to(torch.bfloat16)):
+        ids, u = rank_confidence(src, unl, 2, "entropy", batch_size=1, scorer=scorer)
+        ref = x if not hasattr(src, "dtype") or src.dtype != torch.bfloat16 else src.float().cpu().numpy()
+        want = R.score_pool(ref, "entropy").astype(np.float32)
+        np.testing.assert_allclose(u, want, rtol=RTOL)
+        assert sorted(ids.tolist()) == sorted(np.argsort(want, kind="stable")[:2].tolist())
+
+
+def test_non_default_stream(torch, scorer):
+    """Scoring under `with torch.cuda.stream(side)` is ordered after the producer on that stream, pool_* entries
+    follow torch's current stream too, and alternating streams on one context never share the accumulators in flight."""
+    from oracle import reference_np as R, synth
+    x = synth.synth_logits(1, 0, 6, 64, 96, 19)
+    want = R.score_pool(x, "entropy")
+    side = torch.cuda.Stream()
+    big = torch.empty(64 << 20, device="cuda")
+    for rep in range(3):
+        with torch.cuda.stream(side):
+            big.normal_()                                         # keep `side` busy so a missing dependency would show
+            xt = torch.from_numpy(x).pin_memory().cuda(non_blocking=True)   # produced on `side`
+            xt = xt + 0.0
+            got = scorer.score(xt, "entropy")
+            scorer.pool_begin(6)
+            scorer.pool_score_batch(xt, np.arange(6), "entropy")
+            ids, u = scorer.pool_select(np.arange(6), 3)
+        side.synchronize()
+        assert_scores(got, want)
+        np.testing.assert_allclose(u, want.astype(np.float32), rtol=RTOL)
+        # straight back on the default stream: must wait for the side-stream launch sequence (shared accumulators)
+        y = scorer.synth_logits(1, 7, 6, 64, 96, 19)
+        a = scorer.score(y, "margin")
+        with torch.cuda.stream(side):
+            side.wait_stream(torch.cuda.current_stream())
+            b = scorer.score(y, "margin")
+        torch.cuda.synchronize()
+        assert np.array_equal(_np(a), _np(b))
+        assert_scores(a, R.score_pool(y.cpu().numpy(), "margin"))
+
+
+def test_t16_c66_small(torch, scorer):
+    """BASELINE config 5's class / sample count (C=66, T=16) on small images, f32 and bf16, all four measures."""
+    from oracle import reference_np as R, synth
+    for dtype in ("float32", "bfloat16"):
+        x = synth.synth_logits(16, 2, 2, 12, 16, 66, dtype=dtype)
+        xf = synth.bf16_bits_to_f32(x) if dtype == "bfloat16" else x
+        xt = torch.from_numpy(x.view(np.int16) if dtype == "bfloat16" else x).cuda()
+        if dtype == "bfloat16":
+            xt = xt.view(torch.bfloat16)
+        for measure in MEASURES + ("variance",):
+            out = scorer.pseudo_annotation(xt, measure, threshold=0.5)
+            want = R.pixel_confidence(xf, measure)
+            assert_pix(out["pseudo_confidence"], want, f"T16 C66 {dtype} {measure}")
+            assert_scores(out["pseudo_mean_confidence"], R.image_scores(want), f"T16 C66 {dtype} {measure}")
+
+
+def test_pool_select_rejects_duplicates_and_bad_ids(torch, scorer):
+    scorer.pool_begin(8)
+    with pytest.raises(ValueError):
+        scorer.pool_select(np.array([1, 2, 2, 3]), 2)
+    with pytest.raises(ValueError):
+        scorer.pool_select(np.array([1, 8]), 1)
+    ids, u = scorer.pool_select(np.array([5, 1, 7]), 5)          # k >= M returns all; unvisited examples are 0.0
+    assert ids.tolist() == [1, 5, 7] and np.all(u == 0)
+    # device primitive with duplicated pairs: no out-of-bounds write, the distinct smallest pairs are still found
+    keys = torch.tensor([0.5, 0.25, 0.25, 0.75], device="cuda")
+    idt = torch.tensor([4, 9, 9, 1], device="cuda")
+    ok, oi = scorer.select_smallest(keys, idt, 2)
+    assert len(oi) == 2
 
 
 def test_nan_and_inf_logits(torch, scorer):
