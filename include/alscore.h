@@ -96,6 +96,12 @@ ALS_API int als_measure_from_name(const char* name, int* measure);
 /* Count of this library's kernel launches issued through ctx since creation. */
 ALS_API int64_t als_launch_count(const als_ctx* ctx);
 
+/* Observability: with timing on, every scoring launch sequence of the logits path (scoring kernel + finalize) is
+ * bracketed by CUDA events on its stream; als_last_scoring_ms waits for the last one and returns its device time.
+ * (The reference's only tracing hook is a commented-out tf.RunOptions(FULL_TRACE), train.py:293-294.) */
+ALS_API int als_ctx_enable_timing(als_ctx* ctx, int on);
+ALS_API int als_last_scoring_ms(als_ctx* ctx, float* ms);
+
 /* ---- graph-level boundary (replaces active_learning.py:234-269) ------------------- */
 
 /*
@@ -211,6 +217,19 @@ ALS_API int als_pool_scores(als_ctx* ctx, float* out, int64_t num_examples);
  */
 ALS_API int als_pool_select(als_ctx* ctx, const int64_t* unlabelled, int64_t M, int64_t selection_size,
                     int64_t* out_ids, float* out_unlabelled_conf, int64_t* out_count);
+
+/*
+ * :682-715 in ONE call, for a pool whose logits arrive as one tensor (device or host): als_pool_begin(num_examples) +
+ * als_pool_score_batch(logits, example_index) + als_pool_select(unlabelled, selection_size), with all host-side work done
+ * before the first launch so that a small pool's single scoring launch is not stretched by gaps between calls.
+ *   example_index   HOST int64[N] or NULL (= 0 .. N-1)
+ * Other arguments and results as in the three calls it replaces.  Synchronous.
+ */
+ALS_API int als_rank_pool(als_ctx* ctx, const void* logits, int logits_on_host, int dtype,
+                          int64_t T, int64_t N, int64_t H, int64_t W, int64_t C, int measure,
+                          const int64_t* example_index, int64_t num_examples,
+                          const int64_t* unlabelled, int64_t M, int64_t selection_size,
+                          int64_t* out_ids, float* out_unlabelled_conf, int64_t* out_count);
 
 /*
  * Device-level selection primitive (block-radix select), also used to merge the

@@ -34,6 +34,8 @@ SIGNATURES = {
     "als_last_error": (C.c_char_p, [_p]),
     "als_measure_from_name": (C.c_int, [C.c_char_p, C.POINTER(C.c_int)]),
     "als_launch_count": (_i64, [_p]),
+    "als_ctx_enable_timing": (C.c_int, [_p, C.c_int]),
+    "als_last_scoring_ms": (C.c_int, [_p, C.POINTER(C.c_float)]),
     "als_score": (C.c_int, [_p, _p, C.c_int, _i64, _i64, _i64, _i64, _i64, C.c_int, _p, _p, _p, _p, C.c_float, _p]),
     "als_score_host": (C.c_int, [_p, _p, C.c_int, _i64, _i64, _i64, _i64, _i64, C.c_int, _p, _p, _p, _p, C.c_float]),
     "als_score_dlpack": (C.c_int, [_p, _p, C.c_int, _p, _p]),
@@ -47,6 +49,8 @@ SIGNATURES = {
     "als_pool_score_batch": (C.c_int, [_p, _p, C.c_int, C.c_int, _i64, _i64, _i64, _i64, _i64, C.c_int, _p]),
     "als_pool_scores": (C.c_int, [_p, _p, _i64]),
     "als_pool_select": (C.c_int, [_p, _p, _i64, _i64, _p, _p, C.POINTER(_i64)]),
+    "als_rank_pool": (C.c_int, [_p, _p, C.c_int, C.c_int, _i64, _i64, _i64, _i64, _i64, C.c_int, _p, _i64, _p, _i64, _i64,
+                                _p, _p, C.POINTER(_i64)]),
     "als_select_smallest": (C.c_int, [_p, _p, _p, _i64, _i64, _p, _p, _p]),
     "als_comm_unique_id": (C.c_int, [_p]),
     "als_comm_init_rank": (C.c_int, [_p, C.c_int, C.c_int, _p]),

@@ -23,11 +23,17 @@ from . import _lib
 MEASURES = ("entropy", "margin", "confidence", "variance")
 
 
+_MEASURE_IDS = {}
+
+
 def measure_id(name: str) -> int:
     """Measure name -> C enum; unknown names raise exactly like active_learning.py:259-260."""
+    if name in _MEASURE_IDS:
+        return _MEASURE_IDS[name]
     out = C.c_int(-1)
     rc = _lib.load().als_measure_from_name(str(name).encode(), C.byref(out))
     _lib.check(rc)
+    _MEASURE_IDS[name] = out.value
     return out.value
 
 
@@ -124,6 +130,16 @@ class Scorer:
     @property
     def launch_count(self) -> int:
         return int(self._lib.als_launch_count(self._ctx))
+
+    def enable_timing(self, on: bool = True) -> None:
+        """Bracket every scoring launch sequence of the logits path with CUDA events (see last_scoring_ms)."""
+        self._check(self._lib.als_ctx_enable_timing(self._ctx, 1 if on else 0))
+
+    def last_scoring_ms(self) -> float:
+        """Device time of the last scoring launch sequence (waits for it)."""
+        ms = C.c_float(0.0)
+        self._check(self._lib.als_last_scoring_ms(self._ctx, C.byref(ms)))
+        return float(ms.value)
 
     def _check(self, rc: int) -> None:
         _lib.check(rc, self._ctx)
@@ -363,6 +379,33 @@ class Scorer:
                                               ids.ctypes.data, conf.ctypes.data, C.byref(cnt)))
         return ids[:cnt.value], conf
 
+    def rank_pool(self, logits, unlabelled, selection_size: int, measure: str = "entropy", *, example_index=None,
+                  num_examples: Optional[int] = None, dtype: Optional[str] = None) -> Tuple[np.ndarray, np.ndarray]:
+        """The whole closure (:682-715) in one library call for a pool held in ONE tensor: np.zeros, score + scatter,
+        filter, k lowest.  Returns (low_conf_examples, unlabelled_confidence)."""
+        m = measure_id(measure)
+        lg = _Logits(logits, dtype)
+        unl = np.ascontiguousarray(np.asarray(unlabelled, dtype=np.int64))
+        if unl.ndim != 1:
+            raise ValueError("unlabelled must be a 1-D index array")
+        idx = None
+        if example_index is not None:
+            idx = np.ascontiguousarray(np.asarray(example_index, dtype=np.int64))
+            if idx.shape != (lg.N,):
+                raise ValueError("example_index must have one entry per image (%d), got shape %s" % (lg.N, idx.shape))
+        if num_examples is None:
+            num_examples = int(max(idx.max(initial=-1) if idx is not None else lg.N - 1, unl.max(initial=-1))) + 1
+        k = int(max(0, min(int(selection_size), unl.size)))
+        ids = np.empty(k, np.int64)
+        conf = np.empty(unl.size, np.float32)
+        cnt = C.c_int64(0)
+        self._sync_stream()
+        self._keep = logits
+        self._check(self._lib.als_rank_pool(self._ctx, lg.ptr, 1 if lg.on_host else 0, lg.dtype, lg.T, lg.N, lg.H, lg.W, lg.C, m,
+                                            None if idx is None else idx.ctypes.data, int(num_examples), unl.ctypes.data,
+                                            unl.size, int(selection_size), ids.ctypes.data, conf.ctypes.data, C.byref(cnt)))
+        return ids[:cnt.value], conf
+
     # -- multi-GPU: pool sharded by image (csrc/comm.cu) ------------------------------------------------
     def comm_init(self, rank: int, world: int, unique_id: bytes) -> None:
         """Join the NCCL communicator of a sharded pool pass (one process per GPU).  `unique_id` is the 128-byte id
@@ -565,6 +608,11 @@ def rank_confidence(logits, unlabelled, selection_size: int, measure: str = "ent
     sc = scorer or default_scorer()
     measure_id(measure)   # unknown measure fails before any work, like graph construction does
     unlabelled = np.asarray(unlabelled, dtype=np.int64)
+    if (head_kernel is None and hasattr(logits, "ndim") and hasattr(logits, "shape")
+            and (not batch_size or int(batch_size) >= int(logits.shape[-4]))):
+        # the pool is one tensor and goes through in one batch: the whole closure is one library call
+        return sc.rank_pool(logits, unlabelled, selection_size, measure, example_index=example_index,
+                            num_examples=num_examples, dtype=dtype)
     if hasattr(logits, "ndim") and hasattr(logits, "shape"):
         n = int(logits.shape[-4])
         if example_index is None:

@@ -154,7 +154,7 @@ int check_common(als_ctx* ctx, const void* logits, int dtype, const Shape& s, in
 // Core: device logits -> fixed-point sums -> finalize.  scores64 / pool scatter optional.
 int score_device(als_ctx* ctx, const void* logits, int dtype, const Shape& s, int measure, double* scores64,
                  float* pool32, const long long* example_index_dev, int64_t num_examples, float* conf_map,
-                 uint8_t* label, uint8_t* mask, float threshold, cudaStream_t stream) {
+                 uint8_t* label, uint8_t* mask, float threshold, cudaStream_t stream, int64_t index_base = 0) {
   if (s.N == 0) return ALS_OK;
   const long long P = s.P();
   const int es = dtype == ALS_F32 ? 4 : 2;
@@ -185,11 +185,50 @@ int score_device(als_ctx* ctx, const void* logits, int dtype, const Shape& s, in
   p.conf_map = conf_map;
   p.label = label;
   p.mask = mask;
+  const double inv_scale_p = ldexp(1.0, -shift) / static_cast<double>(P);
+  if (ctx->timing) ALS_CUDA(ctx, cudaEventRecord(ctx->ev_t0, stream));
+  struct TimingEnd {  // closes the timed interval on every return path below
+    als_ctx* c; cudaStream_t st;
+    ~TimingEnd() { if (c->timing) c->timing_valid = cudaEventRecord(c->ev_t1, st) == cudaSuccess; }
+  } timing_end{ctx, stream};
+  if (plan.tiled && s.N <= als::kFusedFinalizeMaxImages) {
+    // small launches: the scoring kernel's last CTA finalizes (one launch per batch instead of two)
+    p.fin_n = static_cast<int>(s.N);
+    p.done_counter = reinterpret_cast<unsigned int*>(ctx->tile_counter + 1);
+    p.fin_inv_scale_p = inv_scale_p;
+    p.fin_scores64 = scores64;
+    p.fin_pool32 = pool32;
+    p.fin_example_index = example_index_dev;
+    p.fin_index_base = index_base;
+    p.fin_num_examples = num_examples;
+    ALS_CUDA(ctx, als::launch_score(plan, dtype, p, stream));
+    ctx->launches += 1;
+    return scratch_end(ctx, stream);
+  }
   ALS_CUDA(ctx, als::launch_score(plan, dtype, p, stream));
-  ALS_CUDA(ctx, als::launch_finalize(ctx->acc, ctx->acc_cap, ctx->flags, ctx->tile_counter, static_cast<int>(s.N), ldexp(1.0, -shift) / static_cast<double>(P),
-                                     scores64, pool32, example_index_dev, num_examples, stream));
+  ALS_CUDA(ctx, als::launch_finalize(ctx->acc, ctx->acc_cap, ctx->flags, ctx->tile_counter, static_cast<int>(s.N), inv_scale_p,
+                                     scores64, pool32, example_index_dev, index_base, num_examples, stream));
   ctx->launches += 2;
   return scratch_end(ctx, stream);
+}
+
+// example_index -> device, unless it is the run first, first+1, ...: then the scatter needs no index vector at all
+// (the usual case when a pool is walked in order; saves the small host->device copy in front of every batch)
+int stage_index(als_ctx* ctx, const int64_t* example_index, int64_t B, const long long** dev, int64_t* base) {
+  bool run = true;
+  for (int64_t i = 1; i < B && run; ++i) run = example_index[i] == example_index[0] + i;
+  if (run) {
+    *dev = nullptr;
+    *base = example_index[0];
+    return ALS_OK;
+  }
+  ALS_TRY(grow(ctx, &ctx->index_dev, &ctx->index_cap, B, false));
+  // (pageable source: staged by the driver before the call returns)
+  ALS_CUDA(ctx, cudaMemcpyAsync(ctx->index_dev, example_index, static_cast<size_t>(B) * sizeof(int64_t), cudaMemcpyHostToDevice,
+                                ctx->stream));
+  *dev = ctx->index_dev;
+  *base = 0;
+  return ALS_OK;
 }
 
 int ensure_acc(als_ctx* ctx, int64_t n) {
@@ -320,7 +359,8 @@ int als_ctx_create(int device, als_ctx** out) {
     ok = cudaEventCreateWithFlags(&ctx->ev_copied[b], cudaEventDisableTiming) == cudaSuccess &&
          cudaEventCreateWithFlags(&ctx->ev_scored[b], cudaEventDisableTiming) == cudaSuccess;
   }
-  ok = ok && cudaEventCreateWithFlags(&ctx->ev_scratch, cudaEventDisableTiming) == cudaSuccess;
+  ok = ok && cudaEventCreateWithFlags(&ctx->ev_scratch, cudaEventDisableTiming) == cudaSuccess &&
+       cudaEventCreateWithFlags(&ctx->ev_unl, cudaEventDisableTiming) == cudaSuccess;
   ok = ok && cudaMalloc(reinterpret_cast<void**>(&ctx->tile_counter), 128) == cudaSuccess &&
        cudaMemset(ctx->tile_counter, 0, 128) == cudaSuccess && cudaDeviceSynchronize() == cudaSuccess;
   if (!ok) {
@@ -347,6 +387,9 @@ int als_ctx_destroy(als_ctx* ctx) {
   if (ctx->sel_ids_host) cudaFreeHost(ctx->sel_ids_host);
   if (ctx->sel_out_host) cudaFreeHost(ctx->sel_out_host);
   if (ctx->ev_scratch) cudaEventDestroy(ctx->ev_scratch);
+  if (ctx->ev_unl) cudaEventDestroy(ctx->ev_unl);
+  if (ctx->ev_t0) cudaEventDestroy(ctx->ev_t0);
+  if (ctx->ev_t1) cudaEventDestroy(ctx->ev_t1);
   for (int b = 0; b < 2; ++b) {
     if (ctx->ev_copied[b]) cudaEventDestroy(ctx->ev_copied[b]);
     if (ctx->ev_scored[b]) cudaEventDestroy(ctx->ev_scored[b]);
@@ -359,6 +402,27 @@ int als_ctx_destroy(als_ctx* ctx) {
 }
 
 int64_t als_launch_count(const als_ctx* ctx) { return ctx ? ctx->launches : 0; }
+
+int als_ctx_enable_timing(als_ctx* ctx, int on) {
+  if (!ctx) return fail(nullptr, ALS_ERR_INVALID, "context is NULL");
+  DeviceGuard g(ctx->device);
+  if (on && !ctx->ev_t0) {
+    ALS_CUDA(ctx, cudaEventCreate(&ctx->ev_t0));
+    ALS_CUDA(ctx, cudaEventCreate(&ctx->ev_t1));
+  }
+  ctx->timing = on != 0;
+  ctx->timing_valid = false;
+  return ALS_OK;
+}
+
+int als_last_scoring_ms(als_ctx* ctx, float* ms) {
+  if (!ctx || !ms) return fail(ctx, ALS_ERR_INVALID, "NULL argument");
+  if (!ctx->timing || !ctx->timing_valid) return fail(ctx, ALS_ERR_STATE, "no timed scoring launch (als_ctx_enable_timing)");
+  DeviceGuard g(ctx->device);
+  ALS_CUDA(ctx, cudaEventSynchronize(ctx->ev_t1));
+  ALS_CUDA(ctx, cudaEventElapsedTime(ms, ctx->ev_t0, ctx->ev_t1));
+  return ALS_OK;
+}
 
 int als_ctx_set_stream(als_ctx* ctx, void* stream) {
   if (!ctx) return fail(nullptr, ALS_ERR_INVALID, "context is NULL");
@@ -529,7 +593,7 @@ int check_features(als_ctx* ctx, const void* features, int64_t T, int64_t N, int
 // device features [T,N,h,w,16] -> fixed-point sums -> finalize (scores64 and/or pool scatter)
 int score_features_device(als_ctx* ctx, const void* features, int64_t T, int64_t N, int64_t h, int64_t w, int measure, double* scores64,
                           float* pool32, const long long* example_index_dev, int64_t num_examples, float* conf_map,
-                          uint8_t* label, uint8_t* mask, float threshold, cudaStream_t stream) {
+                          uint8_t* label, uint8_t* mask, float threshold, cudaStream_t stream, int64_t index_base = 0) {
   if (N == 0) return ALS_OK;
   const int C = static_cast<int>(ctx->head_C);
   als::HeadPlan plan = als::plan_head(C, measure, static_cast<int>(T), ctx->num_sms);
@@ -578,7 +642,7 @@ int score_features_device(als_ctx* ctx, const void* features, int64_t T, int64_t
   ALS_CUDA(ctx, als::launch_head(plan, p, stream));
   ALS_CUDA(ctx, als::launch_finalize(ctx->acc, ctx->acc_cap, ctx->flags, ctx->tile_counter, static_cast<int>(N),
                                      ldexp(1.0, -shift) / static_cast<double>(P), scores64, pool32, example_index_dev,
-                                     num_examples, stream));
+                                     index_base, num_examples, stream));
   ctx->launches += 2;
   return scratch_end(ctx, stream);
 }
@@ -665,7 +729,6 @@ int als_pool_score_features_batch(als_ctx* ctx, const void* features, int featur
                   (long long)example_index[i], (long long)ctx->pool_n);
   DeviceGuard g(ctx->device);
   ALS_TRY(ensure_acc(ctx, B));
-  ALS_TRY(grow(ctx, &ctx->index_dev, &ctx->index_cap, B, false));
   const void* dev = features;
   int b = -1;
   if (features_on_host) {
@@ -677,10 +740,11 @@ int als_pool_score_features_batch(als_ctx* ctx, const void* features, int featur
   } else {
     ALS_TRY(check_device_ptr(ctx, features, "features"));
   }
-  ALS_CUDA(ctx, cudaMemcpyAsync(ctx->index_dev, example_index, static_cast<size_t>(B) * sizeof(int64_t),
-                                cudaMemcpyHostToDevice, ctx->stream));
-  ALS_TRY(score_features_device(ctx, dev, T, B, h, w, measure, nullptr, ctx->pool32, ctx->index_dev, ctx->pool_n, nullptr, nullptr,
-                                nullptr, 0.f, ctx->stream));
+  const long long* idx_dev = nullptr;
+  int64_t idx_base = 0;
+  ALS_TRY(stage_index(ctx, example_index, B, &idx_dev, &idx_base));
+  ALS_TRY(score_features_device(ctx, dev, T, B, h, w, measure, nullptr, ctx->pool32, idx_dev, ctx->pool_n, nullptr, nullptr,
+                                nullptr, 0.f, ctx->stream, idx_base));
   if (b >= 0) {
     ALS_CUDA(ctx, cudaEventRecord(ctx->ev_scored[b], ctx->stream));
     ALS_CUDA(ctx, cudaEventSynchronize(ctx->ev_copied[b]));
@@ -718,7 +782,6 @@ int als_pool_score_batch(als_ctx* ctx, const void* logits, int logits_on_host, i
                   (long long)example_index[i], (long long)ctx->pool_n);
   DeviceGuard g(ctx->device);
   ALS_TRY(ensure_acc(ctx, B));
-  ALS_TRY(grow(ctx, &ctx->index_dev, &ctx->index_cap, B, false));
   static_assert(sizeof(long long) == sizeof(int64_t), "");
   const void* dev_logits = logits;
   int b = -1;
@@ -731,11 +794,11 @@ int als_pool_score_batch(als_ctx* ctx, const void* logits, int logits_on_host, i
   } else {
     ALS_TRY(check_device_ptr(ctx, logits, "logits"));
   }
-  // The index vector rides the compute stream (pageable source: staged by the driver before returning).
-  ALS_CUDA(ctx, cudaMemcpyAsync(ctx->index_dev, example_index, static_cast<size_t>(B) * sizeof(int64_t),
-                                cudaMemcpyHostToDevice, ctx->stream));
-  ALS_TRY(score_device(ctx, dev_logits, dtype, s, measure, nullptr, ctx->pool32, ctx->index_dev, ctx->pool_n, nullptr,
-                       nullptr, nullptr, 0.f, ctx->stream));
+  const long long* idx_dev = nullptr;
+  int64_t idx_base = 0;
+  ALS_TRY(stage_index(ctx, example_index, B, &idx_dev, &idx_base));
+  ALS_TRY(score_device(ctx, dev_logits, dtype, s, measure, nullptr, ctx->pool32, idx_dev, ctx->pool_n, nullptr,
+                       nullptr, nullptr, 0.f, ctx->stream, idx_base));
   if (b >= 0) {
     ALS_CUDA(ctx, cudaEventRecord(ctx->ev_scored[b], ctx->stream));
     // "returns once staged": the caller may reuse its host buffer after this call
@@ -788,7 +851,11 @@ int upload_unlabelled(als_ctx* ctx, const int64_t* unlabelled, int64_t M) {
   ctx->sel_ids_host_cap = static_cast<int64_t>(cap / 8);
   // the previous selection's copy out of this pinned buffer completed before that call returned (it synchronises)
   memcpy(ctx->sel_ids_host, unlabelled, static_cast<size_t>(M) * 8);
-  ALS_CUDA(ctx, cudaMemcpyAsync(ctx->sel_ids, ctx->sel_ids_host, static_cast<size_t>(M) * 8, cudaMemcpyHostToDevice, ctx->stream));
+  // on the copy stream: the upload overlaps the scoring kernels still running on the context's stream, only the
+  // select launch waits for it (the previous selection has been waited for by the host, so sel_ids is free)
+  ALS_CUDA(ctx, cudaMemcpyAsync(ctx->sel_ids, ctx->sel_ids_host, static_cast<size_t>(M) * 8, cudaMemcpyHostToDevice, ctx->copy_stream));
+  ALS_CUDA(ctx, cudaEventRecord(ctx->ev_unl, ctx->copy_stream));
+  ALS_CUDA(ctx, cudaStreamWaitEvent(ctx->stream, ctx->ev_unl, 0));
   return ALS_OK;
 }
 
@@ -804,7 +871,7 @@ SelectBlock select_block(int64_t k, int64_t M) {
 
 int ensure_select_block(als_ctx* ctx, const SelectBlock& b, int64_t kmax) {
   void* p = ctx->sel_out;
-  ALS_TRY(grow_bytes(ctx, &p, &ctx->sel_out_cap, b.bytes));
+  ALS_TRY(grow_bytes(ctx, &p, &ctx->sel_out_cap, 64));  // device scratch for the {count, status} words of helper launches
   ctx->sel_out = static_cast<unsigned char*>(p);
   p = ctx->sel_out_host;
   ALS_TRY(grow_pinned(ctx, &p, &ctx->sel_out_host_cap, b.bytes));
@@ -825,23 +892,25 @@ int ensure_select_block(als_ctx* ctx, const SelectBlock& b, int64_t kmax) {
   return ALS_OK;
 }
 
+// The result block lives in PINNED HOST memory (device-accessible under unified addressing): the select kernel writes
+// count / ids / keys / unlabelled_confidence straight over PCIe, so a pass ends with one kernel and a stream
+// synchronisation -- no separate device->host copy operation.
 SelectOut select_out_of(als_ctx* ctx, const SelectBlock& b, int64_t M) {
   SelectOut o{};
-  o.count = reinterpret_cast<long long*>(ctx->sel_out);
-  o.ids = reinterpret_cast<long long*>(ctx->sel_out + b.off_ids);
-  o.keys = reinterpret_cast<float*>(ctx->sel_out + b.off_keys);
+  o.count = reinterpret_cast<long long*>(ctx->sel_out_host);
+  o.ids = reinterpret_cast<long long*>(ctx->sel_out_host + b.off_ids);
+  o.keys = reinterpret_cast<float*>(ctx->sel_out_host + b.off_keys);
   o.pad_base = -1;
-  o.uconf = reinterpret_cast<float*>(ctx->sel_out + b.off_uconf);
+  o.uconf = reinterpret_cast<float*>(ctx->sel_out_host + b.off_uconf);
   o.uconf_ids = ctx->sel_ids;
   o.uconf_M = M;
   o.uconf_pool = ctx->pool32;
   return o;
 }
 
-// ONE device->host copy of the whole block, then unpack into the caller's arrays.
+// Wait for the select kernel (its writes to the pinned block are visible once the stream is idle), then unpack.
 int fetch_select_block(als_ctx* ctx, const SelectBlock& b, int64_t k, int64_t M, int64_t* out_ids, float* out_unlabelled_conf,
                        int64_t* out_count) {
-  ALS_CUDA(ctx, cudaMemcpyAsync(ctx->sel_out_host, ctx->sel_out, b.bytes, cudaMemcpyDeviceToHost, ctx->stream));
   ALS_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
   const long long* hdr = reinterpret_cast<const long long*>(ctx->sel_out_host);
   if (hdr[1] != 0)
@@ -888,6 +957,40 @@ int als_pool_select(als_ctx* ctx, const int64_t* unlabelled, int64_t M, int64_t 
                                    ctx->stream, &nl));
   ctx->launches += nl;
   return als::fetch_select_block(ctx, blk, k, M, out_ids, out_unlabelled_conf, out_count);
+}
+
+// :682-715 in one call, for a pool that arrives as one tensor.  Same results as begin + score_batch + select; the point
+// is the order of the host work: the scoring launch is queued FIRST, and everything the selection needs from the host
+// (validating and uploading `unlabelled`, growing buffers) happens while the GPU scores, so a small pool -- one scoring
+// launch of a few hundred microseconds -- is followed by the select launch without a host gap.
+int als_rank_pool(als_ctx* ctx, const void* logits, int logits_on_host, int dtype, int64_t T, int64_t N, int64_t H, int64_t W,
+                  int64_t C, int measure, const int64_t* example_index, int64_t num_examples, const int64_t* unlabelled,
+                  int64_t M, int64_t selection_size, int64_t* out_ids, float* out_unlabelled_conf, int64_t* out_count) {
+  const Shape s{T, N, H, W, C};
+  ALS_TRY(check_common(ctx, logits, dtype, s, measure, false));
+  if (num_examples < 0) return fail(ctx, ALS_ERR_INVALID, "num_examples must be >= 0");
+  if (M < 0) return fail(ctx, ALS_ERR_INVALID, "M must be >= 0");
+  if (!out_count) return fail(ctx, ALS_ERR_INVALID, "out_count is NULL");
+  *out_count = 0;
+  if (M > 0 && !unlabelled) return fail(ctx, ALS_ERR_INVALID, "unlabelled is NULL");
+  if (!example_index && N > num_examples) return fail(ctx, ALS_ERR_INVALID, "the pool holds %lld examples but %lld images were given",
+                                                      (long long)num_examples, (long long)N);
+  const int64_t k = selection_size < 0 ? 0 : (selection_size < M ? selection_size : M);  // :707-708
+  if (k > 0 && !out_ids) return fail(ctx, ALS_ERR_INVALID, "out_ids is NULL");
+  DeviceGuard g(ctx->device);
+  ALS_TRY(als_pool_begin(ctx, num_examples));  // :684-685
+  if (N > 0) {
+    std::vector<int64_t> iota;
+    const int64_t* idx = example_index;
+    if (!idx) {  // examples 0 .. N-1 in order
+      iota.resize(static_cast<size_t>(N));
+      for (int64_t i = 0; i < N; ++i) iota[static_cast<size_t>(i)] = i;
+      idx = iota.data();
+    }
+    ALS_TRY(als_pool_score_batch(ctx, logits, logits_on_host, dtype, T, N, H, W, C, measure, idx));  // :697-700
+  }
+  // the GPU is scoring; the host prepares the selection meanwhile
+  return als_pool_select(ctx, unlabelled, M, selection_size, out_ids, out_unlabelled_conf, out_count);  // :705-715
 }
 
 int als_select_smallest(als_ctx* ctx, const float* keys, const int64_t* ids, int64_t M, int64_t k, float* out_keys,
@@ -1023,7 +1126,7 @@ int als_mc_add_sample(als_ctx* ctx, const void* logits, int logits_on_host) {
   const Shape s{1, ctx->mc_N, ctx->mc_H, ctx->mc_W, ctx->mc_C};
   const int es = ctx->mc_dtype == ALS_F32 ? 4 : 2;
   const void* dev = logits;
-  int b = -1;
+  int b = -1, d2d = -1;
   if (logits_on_host) {
     ALS_TRY(ensure_stage(ctx, static_cast<size_t>(s.elems()) * es));
     ALS_TRY(stage_chunk(ctx, static_cast<const unsigned char*>(logits), s, es, 0, s.N, &b));
@@ -1032,13 +1135,21 @@ int als_mc_add_sample(als_ctx* ctx, const void* logits, int logits_on_host) {
   } else {
     ALS_TRY(check_device_ptr(ctx, logits, "logits"));
   }
-  // one layout for the whole accumulation: a misaligned sample forces the generic kernels from the first sample on
-  const bool aligned = reinterpret_cast<uintptr_t>(dev) % 16 == 0;
-  const als::McPlan plan = als::plan_mc(ctx->mc_dtype, static_cast<int>(s.C), s.N * s.P(), aligned && ctx->mc_tiled != 0,
-                                        ctx->num_sms, ctx->max_smem);
-  if (ctx->mc_tiled < 0) ctx->mc_tiled = plan.tiled ? 1 : 0;
-  else if ((ctx->mc_tiled == 1) != plan.tiled)
-    return fail(ctx, ALS_ERR_INVALID, "samples of one accumulation must all be 16-byte aligned (or none of them)");
+  // One state layout for the whole accumulation (the tiled one whenever a specialised kernel exists).  The bulk copies
+  // of the tiled kernel need a 16-byte aligned sample: a misaligned device sample (e.g. slice t of an odd-sized
+  // [T,N,H,W,C] stack) is first copied, device to device, into the aligned staging buffer -- a rare path.
+  als::McPlan plan = als::plan_mc(ctx->mc_dtype, static_cast<int>(s.C), s.N * s.P(), true, ctx->num_sms, ctx->max_smem);
+  ctx->mc_tiled = plan.tiled ? 1 : 0;
+  if (plan.tiled && reinterpret_cast<uintptr_t>(dev) % 16 != 0) {
+    const size_t bytes = static_cast<size_t>(s.elems()) * es;
+    ALS_TRY(ensure_stage(ctx, bytes));
+    const int sb = ctx->stage_next;
+    ctx->stage_next ^= 1;
+    ALS_CUDA(ctx, cudaStreamWaitEvent(ctx->stream, ctx->ev_scored[sb], 0));
+    ALS_CUDA(ctx, cudaMemcpyAsync(ctx->stage[sb], dev, bytes, cudaMemcpyDeviceToDevice, ctx->stream));
+    dev = ctx->stage[sb];
+    d2d = sb;  // ev_scored[sb] is recorded below so that the next user of this staging buffer waits for the kernel
+  }
   als::ScoreParams p{};
   p.logits = dev;
   p.total_pixels = s.N * s.P();
@@ -1046,6 +1157,7 @@ int als_mc_add_sample(als_ctx* ctx, const void* logits, int logits_on_host) {
   p.T = 1;
   p.C = static_cast<int>(s.C);
   p.tile_counter = ctx->tile_counter;
+  p.done_counter = reinterpret_cast<unsigned int*>(ctx->tile_counter + 1);
   p.acc = ctx->acc;
   p.acc_stride = ctx->acc_cap;
   p.flags = ctx->flags;
@@ -1054,6 +1166,7 @@ int als_mc_add_sample(als_ctx* ctx, const void* logits, int logits_on_host) {
   ALS_CUDA(ctx, als::launch_mc_update(plan, ctx->mc_dtype, p, ctx->mc_state, static_cast<int>(ctx->mc_samples), ctx->stream));
   ctx->launches += 1;
   ALS_TRY(scratch_end(ctx, ctx->stream));
+  if (d2d >= 0) ALS_CUDA(ctx, cudaEventRecord(ctx->ev_scored[d2d], ctx->stream));
   if (b >= 0) {
     ALS_CUDA(ctx, cudaEventRecord(ctx->ev_scored[b], ctx->stream));
     ALS_CUDA(ctx, cudaEventSynchronize(ctx->ev_copied[b]));  // "returns once staged"
@@ -1083,11 +1196,9 @@ int als_mc_finish(als_ctx* ctx, int measure, double* scores, const int64_t* exam
   ALS_TRY(check_device_ptr(ctx, scores, "scores"));
   ALS_TRY(check_device_ptr(ctx, conf_map, "conf_map"));
   ALS_TRY(check_device_ptr(ctx, mask, "mask"));
-  if (example_index) {
-    ALS_TRY(grow(ctx, &ctx->index_dev, &ctx->index_cap, s.N, false));
-    ALS_CUDA(ctx, cudaMemcpyAsync(ctx->index_dev, example_index, static_cast<size_t>(s.N) * sizeof(int64_t), cudaMemcpyHostToDevice,
-                                  ctx->stream));
-  }
+  const long long* idx_dev = nullptr;
+  int64_t idx_base = 0;
+  if (example_index) ALS_TRY(stage_index(ctx, example_index, s.N, &idx_dev, &idx_base));
   const als::McPlan plan = als::plan_mc(ctx->mc_dtype, static_cast<int>(s.C), s.N * s.P(), ctx->mc_tiled == 1, ctx->num_sms,
                                         ctx->max_smem);
   const long long P = s.P();
@@ -1113,7 +1224,7 @@ int als_mc_finish(als_ctx* ctx, int measure, double* scores, const int64_t* exam
   ALS_CUDA(ctx, als::launch_mc_finish(plan, ctx->mc_dtype, p, ctx->mc_state, ctx->stream));
   ALS_CUDA(ctx, als::launch_finalize(ctx->acc, ctx->acc_cap, ctx->flags, ctx->tile_counter, static_cast<int>(s.N),
                                      ldexp(1.0, -shift) / static_cast<double>(P), scores, example_index ? ctx->pool32 : nullptr,
-                                     example_index ? ctx->index_dev : nullptr, example_index ? ctx->pool_n : 0, ctx->stream));
+                                     idx_dev, idx_base, example_index ? ctx->pool_n : 0, ctx->stream));
   ctx->launches += 2;
   return scratch_end(ctx, ctx->stream);
 }

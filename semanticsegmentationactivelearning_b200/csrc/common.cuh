@@ -137,6 +137,35 @@ __device__ __forceinline__ float hsum2(f32x2 v) {
   return lo + hi;
 }
 
+// ---- exp2 on the FMA pipe (bring-up option ALS_POLY_PAIRS, measured in DESIGN.md; the shipped build does not use it) ----
+// Two exp2 per call without touching the MUFU (XU) pipe: round-to-nearest split t = n + f by the 1.5*2^23 magic add,
+// degree-6 polynomial for 2^f on [-0.5, 0.5] (relative error 2.4e-7 in fp32, the same as ex2.approx), exponent inserted with an integer shift-add.
+// t is clamped at -126 (2^t flushes to ~1e-38 there, like ex2.approx.ftz returns 0 a little further down).
+// Cost: 3 + 6 packed FMA-pipe instructions + 2 FMNMX + 2 LEA for two results, against 2 MUFU.EX2 issue slots.
+__device__ __forceinline__ f32x2 ex2_poly2(f32x2 t2) {
+  float t0, t1;
+  unpack2(t2, t0, t1);
+  t2 = pack2(fmaxf(t0, -126.0f), fmaxf(t1, -126.0f));
+  const f32x2 magic = pack2(12582912.0f, 12582912.0f), nmagic = pack2(-12582912.0f, -12582912.0f);
+  const f32x2 one = pack2(1.0f, 1.0f), mone = pack2(-1.0f, -1.0f);
+  const f32x2 r2 = add2(t2, magic);          // low mantissa bits = n = round(t)
+  const f32x2 n2 = add2(r2, nmagic);         // n as a float (exact)
+  const f32x2 f2 = fma2(n2, mone, t2);       // f = t - n in [-0.5, 0.5]
+  f32x2 p = pack2(1.5403530e-4f, 1.5403530e-4f);
+  p = fma2(p, f2, pack2(1.3333558e-3f, 1.3333558e-3f));
+  p = fma2(p, f2, pack2(9.6181291e-3f, 9.6181291e-3f));
+  p = fma2(p, f2, pack2(5.5504109e-2f, 5.5504109e-2f));
+  p = fma2(p, f2, pack2(2.4022651e-1f, 2.4022651e-1f));
+  p = fma2(p, f2, pack2(6.9314718e-1f, 6.9314718e-1f));
+  p = fma2(p, f2, one);
+  float p0, p1, r0, r1;
+  unpack2(p, p0, p1);
+  unpack2(r2, r0, r1);
+  p0 = __uint_as_float(__float_as_uint(p0) + (__float_as_uint(r0) << 23));
+  p1 = __uint_as_float(__float_as_uint(p1) + (__float_as_uint(r1) << 23));
+  return pack2(p0, p1);
+}
+
 // max that propagates NaN (fmaxf drops it): keeps a NaN logit visible after the -inf clamp
 __device__ __forceinline__ float max_nan(float a, float b) {
   float y;

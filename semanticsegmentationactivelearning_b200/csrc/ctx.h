@@ -26,6 +26,11 @@ struct als_ctx {
   unsigned long long* tile_counter = nullptr;
   int64_t acc_cap = 0;
   cudaEvent_t ev_scratch = nullptr;
+  cudaEvent_t ev_unl = nullptr;  // unlabelled ids uploaded (copy stream)
+  // optional timing of the scoring launches (als_ctx_enable_timing): events around the last scoring launch sequence
+  bool timing = false;
+  bool timing_valid = false;
+  cudaEvent_t ev_t0 = nullptr, ev_t1 = nullptr;
   cudaStream_t scratch_stream = nullptr;
   bool scratch_used = false;
   // device scratch for scores / indices

@@ -150,12 +150,32 @@ struct Geom {
   // the rows out (the group only splits and stores them), and the warps saved buy registers for the epilogue:
   // T = 1: 576 threads / 96 registers, +2.5 % at C = 19 and +8 % at C = 6 against two groups;  T > 1 (two rows per
   // accumulator): 448 threads / 128 registers with two pixels per epilogue thread, +8 % against 832 threads.
+#ifdef ALS_HEAD_LOADER_GROUPS_MC  // bring-up: loader groups of the T > 1 kernel
+  static constexpr int LOADER_GROUPS = MULTI ? ALS_HEAD_LOADER_GROUPS_MC : 1;
+#else
   static constexpr int LOADER_GROUPS = 1;
+#endif
   static_assert(LOADER_GROUPS <= kMaxLoaderGroups, "loader groups");
   static constexpr int MMA_WARP = FIRST_LOADER_WARP + 4 * LOADER_GROUPS;
   static constexpr int PRODUCER_WARP = MMA_WARP + 1;
+#ifdef ALS_HEAD_MC_SETMAXNREG
+  // bring-up: T > 1 with register re-allocation between the roles (setmaxnreg works on warpgroups of 4 warps: the
+  // MMA / producer warps get two idle companions so that every role is a whole number of warpgroups)
+  static constexpr bool REALLOC = MULTI;
+  static constexpr int THREADS = MULTI ? 32 * (MMA_WARP + 4) : 32 * (PRODUCER_WARP + 1);
+#else
+  static constexpr bool REALLOC = false;
   static constexpr int THREADS = 32 * (PRODUCER_WARP + 1);   // 576 (3 stages) or 448 (2 stages); T > 1: 448 (EPB = 2)
+#endif
 };
+
+#ifndef ALS_HEAD_REGS_EPI
+#define ALS_HEAD_REGS_EPI 128
+#define ALS_HEAD_REGS_LOADER 72
+#define ALS_HEAD_REGS_MMA 56
+#endif
+template <int N> __device__ __forceinline__ void setmaxnreg_inc() { asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(N)); }
+template <int N> __device__ __forceinline__ void setmaxnreg_dec() { asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(N)); }
 
 // TMEM -> registers, CNT consecutive columns (CNT multiple of 4, <= 32)
 template <int CNT>
@@ -202,6 +222,18 @@ __device__ __forceinline__ void ld_cols(uint32_t taddr, float (&v)[CNT]) {
 // two packed FMA-pipe instructions per element pair each.  lo (|lo| <= 2^-11 |x|) is left to the hardware's
 // truncation: an error of at most 2^-21 |x|, the same order as the dropped lo*lo term.
 __device__ __forceinline__ void split_hi_lo(const float4 (&v)[4], uint32_t (&hi)[16], uint32_t (&lo)[16]) {
+#ifdef ALS_HEAD_TRUNC_SPLIT
+  // bring-up: let the tensor core's own truncation make hi (pass x itself), lo = x - trunc13(x): one LOP + one FADD
+  // per element instead of Veltkamp's four FMAs per pair; |lo| < 2^-10 |x| instead of <= 2^-11 |x|
+  const float* f = reinterpret_cast<const float*>(v);
+#pragma unroll
+  for (int i = 0; i < 16; ++i) {
+    const uint32_t u = __float_as_uint(f[i]);
+    hi[i] = u;
+    lo[i] = __float_as_uint(f[i] - __uint_as_float(u & 0xffffe000u));
+  }
+  return;
+#endif
   const f32x2 k2 = pack2(8193.0f, 8193.0f), m1 = pack2(-1.0f, -1.0f);
 #pragma unroll
   for (int c = 0; c < 4; ++c) {
@@ -276,6 +308,9 @@ score_head_kernel(const HeadParams p, const __grid_constant__ CUtensorMap feat_m
   const uint32_t tmem = *tmem_slot;
   pdl_launch_dependents();  // the finalize kernel behind this one may become resident now (it waits for our sums)
 
+  if (warp >= kMmaWarp) {
+  // (REALLOC builds: this warpgroup = MMA issuer, producer and two idle companions; it gives registers back)
+  if constexpr (G::REALLOC) setmaxnreg_dec<ALS_HEAD_REGS_MMA>();
   if (warp == kProducerWarp) {
     // ===== producer =====
     if (lane == 0) {
@@ -402,8 +437,10 @@ score_head_kernel(const HeadParams p, const __grid_constant__ CUtensorMap feat_m
         }
       }
     }
+  }
   } else if (warp >= kFirstLoaderWarp) {
     // ===== loaders: raw NHWC row -> chunk planes (shared) -> hi / lo A rows in tensor memory =====
+    if constexpr (G::REALLOC) setmaxnreg_dec<ALS_HEAD_REGS_LOADER>();
     const int grp = (warp - kFirstLoaderWarp) >> 2;      // rows alternate between the two groups
     const int lt = threadIdx.x - 32 * kFirstLoaderWarp - grp * kLoaderThreads;  // 0..127 inside the group
     const int quarter = warp & 3;                        // TMEM lane quarter this warp may write
@@ -542,6 +579,7 @@ score_head_kernel(const HeadParams p, const __grid_constant__ CUtensorMap feat_m
   } else {
     // ===== epilogue, T samples: every warp takes its EPB blocks of EVERY accumulator; the running mean of the
     // softmax (per class) and the summed M2 of its pixels stay in registers over the T samples of a tile =====
+    if constexpr (G::REALLOC) setmaxnreg_inc<ALS_HEAD_REGS_EPI>();
     const int quarter = warp & 3;             // TMEM lane quarter this warp may read
     const int blk0 = (warp >> 2) * EPB;       // first accumulator block (quad pixel) of this warp
     const int m = quarter * 32 + lane;

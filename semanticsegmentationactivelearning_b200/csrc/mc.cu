@@ -12,6 +12,11 @@
 // welford_update() the resident kernel runs in registers, and writes the state back.  f32 loads / stores are exact, so
 // the final confidences and per-image scores are bit-identical to the resident path.
 //
+// The state is read and written with .cg accesses (L2 only): tiles are claimed dynamically, so the SM that reads a
+// tile's state in launch t+1 is usually not the one that wrote it in launch t, and with programmatic dependent launch
+// the next grid's CTAs become resident while the previous grid still runs -- an L1 line left from an earlier launch
+// must never satisfy a state load (found by the full-geometry parity test: bit-identical on small pools, not on large).
+//
 // State layout (tiled kernels): one block of PPT * (CL + 1) * 256 floats per tile, indexed
 // [pixel slot k][class j | M2][consumer thread], so every load / store of a warp is one coalesced 128-byte line.
 // Algorithmic bytes per pixel and sample: C*sizeof(E) logits read + (C+1)*4 state read (not for sample 0)
@@ -41,6 +46,7 @@ __global__ void __launch_bounds__(kBlockThreads, Cfg<E, C, true>::MINB) mc_updat
   constexpr int CL = K::CL, LPP = K::LPP, PPT = K::PPT, G = K::G, ES = K::ES;
 
   extern __shared__ __align__(128) unsigned char smem[];
+  __shared__ int s_last;
   uint64_t* full = reinterpret_cast<uint64_t*>(smem);
   uint64_t* empty = full + kMaxStages;
   TileMeta* meta = reinterpret_cast<TileMeta*>(smem + 128);
@@ -70,7 +76,6 @@ __global__ void __launch_bounds__(kBlockThreads, Cfg<E, C, true>::MINB) mc_updat
   const int pl = tid / LPP;
   const int class0 = sub * CL;
   const int nvalid = K::EXACT ? CL : min(CL, C - class0);
-  const unsigned int run_off = (pl * C + class0) * ES;
   const float inv_t = __frcp_rn(static_cast<float>(t + 1));  // as in score_tiles_kernel<kMulti>
 
   int s = 0;
@@ -88,8 +93,8 @@ __global__ void __launch_bounds__(kBlockThreads, Cfg<E, C, true>::MINB) mc_updat
 #pragma unroll
       for (int k = 0; k < PPT; ++k) {
 #pragma unroll
-        for (int j = 0; j < CL; ++j) nmu[k][j] = __ldcs(stp + (k * L::ROW + j) * kConsumerThreads);
-        m2s[k] = __ldcs(stp + (k * L::ROW + CL) * kConsumerThreads);
+        for (int j = 0; j < CL; ++j) nmu[k][j] = __ldcg(stp + (k * L::ROW + j) * kConsumerThreads);
+        m2s[k] = __ldcg(stp + (k * L::ROW + CL) * kConsumerThreads);
       }
     } else {
 #pragma unroll
@@ -100,12 +105,7 @@ __global__ void __launch_bounds__(kBlockThreads, Cfg<E, C, true>::MINB) mc_updat
       }
     }
     float x[PPT][CL];
-    const unsigned char* st = stage_base + static_cast<size_t>(s) * K::STAGE_BYTES + run_off;
-#pragma unroll
-    for (int k = 0; k < PPT; ++k) {
-      if constexpr (K::EXACT) load_run<E, CL, K::VB>(st + k * (G * C * ES), x[k]);
-      else load_run_partial<E, CL>(st + k * (G * C * ES), x[k], nvalid);
-    }
+    load_tile_pixels<K, E, C>(stage_base + static_cast<size_t>(s) * K::STAGE_BYTES, pl, class0, nvalid, x);
     __syncwarp();
     if (lane == 0) mbar_arrive(&empty[s]);
     if (++s == nstage) { s = 0; ph ^= 1u; }
@@ -115,15 +115,21 @@ __global__ void __launch_bounds__(kBlockThreads, Cfg<E, C, true>::MINB) mc_updat
       if constexpr (FIRST) {
         if (p.label) {  // pseudo_label = argmax of sample 0 (active_learning.py:234-236)
           const int lbl = group_argmax<CL, LPP>(x[k], nvalid, class0);
-          const int l = k * G + pl;
+          const int l = K::slot(k, pl);
           if (sub == 0 && l < npix) p.label[tile_pix0 + l] = static_cast<uint8_t>(lbl);
         }
       }
       welford_update<CL, LPP, K::EXACT>(x[k], nvalid, inv_t, nmu[k], m2s[k]);
 #pragma unroll
-      for (int j = 0; j < CL; ++j) __stcs(stp + (k * L::ROW + j) * kConsumerThreads, nmu[k][j]);
-      __stcs(stp + (k * L::ROW + CL) * kConsumerThreads, m2s[k]);
+      for (int j = 0; j < CL; ++j) __stcg(stp + (k * L::ROW + j) * kConsumerThreads, nmu[k][j]);
+      __stcg(stp + (k * L::ROW + CL) * kConsumerThreads, m2s[k]);
     }
+  }
+  // the last CTA re-arms the dynamic tile scheduler for the next launch on this stream (kernel -> kernel ordering only:
+  // a stream-ordered memset between two programmatically dependent launches is not something to rely on)
+  if (last_cta_ticket(p.done_counter, &s_last) && threadIdx.x == 0) {
+    *p.tile_counter = 0ull;
+    *p.done_counter = 0u;
   }
 }
 
@@ -158,10 +164,10 @@ __global__ void __launch_bounds__(kConsumerThreads, 3) mc_finish_kernel(const Sc
     for (int k = 0; k < PPT; ++k) {
       float nmu[CL];
 #pragma unroll
-      for (int j = 0; j < CL; ++j) nmu[j] = __ldcs(stp + (k * L::ROW + j) * kConsumerThreads);
-      const float m2s = __ldcs(stp + (k * L::ROW + CL) * kConsumerThreads);
+      for (int j = 0; j < CL; ++j) nmu[j] = __ldcg(stp + (k * L::ROW + j) * kConsumerThreads);
+      const float m2s = __ldcg(stp + (k * L::ROW + CL) * kConsumerThreads);
       const float conf = conf_multi<CL, LPP, K::EXACT>(nmu, m2s, nvalid, p);
-      const int l = k * G + pl;
+      const int l = K::slot(k, pl);
       if (plain) {
         if (sub == 0) acc.add(conf, p.fx_scale);
       } else if (sub == 0 && l < npix) {
@@ -291,7 +297,7 @@ McPlan plan_mc(int dtype, int C, long long total_pixels, bool aligned, int num_s
     const int ctas_per_sm = plan.grid;
     int per_cta = (228 * 1024) / ctas_per_sm - 1024;
     if (per_cta > max_smem_per_block) per_cta = max_smem_per_block;
-    int stages = (per_cta - kSmemHeader) / stage_bytes;
+    int stages = (per_cta - kSmemHeader - 128) / stage_bytes;
     if (stages > kMaxStages) stages = kMaxStages;
     if (stages >= 2) {
       plan.tiled = true;
@@ -301,12 +307,7 @@ McPlan plan_mc(int dtype, int C, long long total_pixels, bool aligned, int num_s
       const long long tiles = (total_pixels + plan.tile_pixels - 1) / plan.tile_pixels;
       int per_sm = 0;
       for (const void* f : {plan.first, plan.update}) {
-        int n = 0;
-        if (cudaFuncSetAttribute(f, cudaFuncAttributeMaxDynamicSharedMemorySize, plan.smem_bytes) != cudaSuccess ||
-            cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, f, plan.block, plan.smem_bytes) != cudaSuccess || n < 1) {
-          (void)cudaGetLastError();
-          n = 1;
-        }
+        const int n = resident_ctas(f, plan.block, plan.smem_bytes);
         per_sm = per_sm == 0 ? n : (n < per_sm ? n : per_sm);
       }
       const long long resident = static_cast<long long>(per_sm) * num_sms;
@@ -336,8 +337,6 @@ cudaError_t launch_mc_update(const McPlan& plan, int dtype, ScoreParams p, float
   p.sample_stride = 0;
   p.any_out = 0;
   if (plan.tiled) {
-    cudaError_t err = cudaMemsetAsync(p.tile_counter, 0, sizeof(unsigned long long), stream);
-    if (err != cudaSuccess) return err;
     p.stages = plan.stages;
     p.num_tiles = (p.total_pixels + plan.tile_pixels - 1) / plan.tile_pixels;
     void* args[] = {&p, &state, &t};

@@ -22,7 +22,7 @@ struct McPlan {
 McPlan plan_mc(int dtype, int C, long long total_pixels, bool aligned, int num_sms, int max_smem_per_block);
 
 // p: logits = this sample ([N,P,C]), T/sample_stride ignored; label (optional) is written by sample 0.
-// Zeroes p.tile_counter itself (stream-ordered) before the launch.
+// p.tile_counter / p.done_counter must be zero on entry; the kernel's last CTA re-zeroes them.
 cudaError_t launch_mc_update(const McPlan& plan, int dtype, ScoreParams p, float* state, int t, cudaStream_t stream);
 // p: measure / inv_T / conf_map / mask / acc as for launch_score; the caller runs launch_finalize afterwards.
 cudaError_t launch_mc_finish(const McPlan& plan, int dtype, ScoreParams p, const float* state, cudaStream_t stream);

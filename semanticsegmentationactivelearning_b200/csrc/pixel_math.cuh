@@ -11,6 +11,18 @@ namespace als {
 
 enum : int { kEntropy = 0, kMargin = 1, kConfidence = 2, kVariance = 3, kMulti = 4 };
 
+// Bring-up knob: the first ALS_POLY_PAIRS class pairs of a pixel take their exp2 from ex2_poly2 (FMA pipe) instead of
+// MUFU.EX2 (XU pipe).  0 in the shipped library -- see DESIGN.md for what the split measured.
+#ifndef ALS_POLY_PAIRS
+#define ALS_POLY_PAIRS 0
+#endif
+__device__ __forceinline__ f32x2 ex2_pair(f32x2 t2, int pair_index) {
+  if (pair_index < ALS_POLY_PAIRS) return ex2_poly2(t2);
+  float t0, t1;
+  unpack2(t2, t0, t1);
+  return pack2(ex2_approx(t0), ex2_approx(t1));
+}
+
 // ---- per-pixel math ---------------------------------------------------------------------
 // top-2 merge across the LPP lanes of a pixel
 template <int LPP>
@@ -61,9 +73,7 @@ __device__ __forceinline__ float entropy_conf(const float (&x)[CL], int nvalid, 
 #pragma unroll
     for (int j = 0; j + 1 < CL; j += 2) {
       const f32x2 t2 = fma2(pack2(x[j], x[j + 1]), l2, nml2);
-      float t0, t1;
-      unpack2(t2, t0, t1);
-      const f32x2 e2 = pack2(ex2_approx(t0), ex2_approx(t1));
+      const f32x2 e2 = ex2_pair(t2, j / 2);
       S2 = add2(S2, e2);
       A2 = fma2(e2, t2, A2);
     }
@@ -105,9 +115,7 @@ __device__ __forceinline__ float exp_sum(const float (&x)[CL], int nvalid, float
     f32x2 S2 = pack2(0.f, 0.f);
 #pragma unroll
     for (int j = 0; j + 1 < CL; j += 2) {
-      float t0, t1;
-      unpack2(fma2(pack2(x[j], x[j + 1]), l2, nml2), t0, t1);
-      S2 = add2(S2, pack2(ex2_approx(t0), ex2_approx(t1)));
+      S2 = add2(S2, ex2_pair(fma2(pack2(x[j], x[j + 1]), l2, nml2), j / 2));
     }
     S = hsum2(S2);
     if constexpr (CL & 1) S += ex2_approx(fmaf(x[CL - 1], kLog2e, -ml));

@@ -20,11 +20,62 @@
 #include <float.h>
 #include <stdlib.h>
 
+#include <mutex>
+#include <vector>
+
 #include "common.cuh"
 #include "pixel_math.cuh"
 #include "tiles.cuh"
 
 namespace als {
+
+// ---- finalize: fixed point -> f64 mean (:261-263), f32 scatter by example index (:700) -------
+__device__ __forceinline__ void finalize_image(int i, long long* __restrict__ acc, long long acc_stride,
+                                               unsigned int* __restrict__ flags, double inv_scale_p,
+                                               double* __restrict__ scores64, float* __restrict__ pool32,
+                                               const long long* __restrict__ example_index, long long index_base,
+                                               long long num_examples) {
+  long long total = 0;
+#pragma unroll 8
+  for (int r = 0; r < kAccReplicas; ++r) {
+    total += __ldcg(acc + r * acc_stride + i);  // L2: the sums were made by REDs of other SMs
+    acc[r * acc_stride + i] = 0;
+  }
+  const double s = __ldcg(flags + i) ? __longlong_as_double(0x7ff8000000000000ll) : static_cast<double>(total) * inv_scale_p;
+  flags[i] = 0;
+  if (scores64) scores64[i] = s;
+  if (pool32) {
+    const long long e = example_index ? example_index[i] : index_base + i;
+    if (e >= 0 && e < num_examples) pool32[e] = static_cast<float>(s);  // f64 -> f32 round-to-nearest
+  }
+}
+
+__global__ void finalize_kernel(long long* __restrict__ acc, long long acc_stride, unsigned int* __restrict__ flags,
+                                unsigned long long* __restrict__ tile_counter, int n, double inv_scale_p,
+                                double* __restrict__ scores64, float* __restrict__ pool32,
+                                const long long* __restrict__ example_index, long long index_base, long long num_examples) {
+  pdl_launch_dependents();
+  pdl_wait();  // the scoring kernel's sums are complete and visible
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i == 0) *tile_counter = 0ull;  // ready for the next scoring launch on this stream
+  if (i >= n) return;
+  finalize_image(i, acc, acc_stride, flags, inv_scale_p, scores64, pool32, example_index, index_base, num_examples);
+}
+
+// Fused finalize: every CTA counts itself done once all its consumer warps have flushed their sums; the CTA that
+// finds itself last (classic "last block" reduction: fence, atomic ticket, fence) does finalize_kernel's work for the
+// whole launch.  One launch less per batch: ~3 us of a 50 us batch-of-8 call, and one dependency edge less in front of
+// the selection.  Consumer threads only (the producer warp has returned): named barrier 1.
+__device__ __forceinline__ void fused_finalize(const ScoreParams& p, int* s_last) {
+  if (!last_cta_ticket(p.done_counter, s_last)) return;
+  for (int i = threadIdx.x; i < p.fin_n; i += kConsumerThreads)
+    finalize_image(i, p.acc, p.acc_stride, p.flags, p.fin_inv_scale_p, p.fin_scores64, p.fin_pool32, p.fin_example_index,
+                   p.fin_index_base, p.fin_num_examples);
+  if (threadIdx.x == 0) {  // ready for the next scoring launch on this stream
+    *p.tile_counter = 0ull;
+    *p.done_counter = 0u;
+  }
+}
 
 template <typename E, int C, int MEASURE>
 __global__ void __launch_bounds__(kBlockThreads, Cfg<E, C, (MEASURE == kMulti)>::MINB) score_tiles_kernel(const ScoreParams p) {
@@ -33,6 +84,7 @@ __global__ void __launch_bounds__(kBlockThreads, Cfg<E, C, (MEASURE == kMulti)>:
   constexpr int CL = K::CL, LPP = K::LPP, PPT = K::PPT, G = K::G, ES = K::ES;
 
   extern __shared__ __align__(128) unsigned char smem[];
+  __shared__ int s_last;
   uint64_t* full = reinterpret_cast<uint64_t*>(smem);
   uint64_t* empty = full + kMaxStages;
   TileMeta* meta = reinterpret_cast<TileMeta*>(smem + 128);
@@ -67,7 +119,6 @@ __global__ void __launch_bounds__(kBlockThreads, Cfg<E, C, (MEASURE == kMulti)>:
   const int pl = tid / LPP;
   const int class0 = sub * CL;
   const int nvalid = K::EXACT ? CL : min(CL, C - class0);
-  const unsigned int run_off = (pl * C + class0) * ES;
 
   ImageAcc acc;
   int s = 0;
@@ -89,14 +140,9 @@ __global__ void __launch_bounds__(kBlockThreads, Cfg<E, C, (MEASURE == kMulti)>:
 
     if constexpr (!MULTI) {
       float x[PPT][CL];
-      const unsigned char* st = stage_base + static_cast<size_t>(s) * K::STAGE_BYTES + run_off;
       // Pixel slots past the end of the pool (last tile only) hold stale but in-bounds bytes:
       // they are computed like the rest (no divergence around the shuffles) and dropped at emit.
-#pragma unroll
-      for (int k = 0; k < PPT; ++k) {
-        if constexpr (K::EXACT) load_run<E, CL, K::VB>(st + k * (G * C * ES), x[k]);
-        else load_run_partial<E, CL>(st + k * (G * C * ES), x[k], nvalid);
-      }
+      load_tile_pixels<K, E, C>(stage_base + static_cast<size_t>(s) * K::STAGE_BYTES, pl, class0, nvalid, x);
       __syncwarp();
       if (lane == 0) mbar_arrive(&empty[s]);  // values are in registers: hand the stage back
       if (++s == nstage) { s = 0; ph ^= 1u; }
@@ -121,7 +167,7 @@ __global__ void __launch_bounds__(kBlockThreads, Cfg<E, C, (MEASURE == kMulti)>:
       } else {
 #pragma unroll
         for (int k = 0; k < PPT; ++k) {
-          const int l = k * G + pl;
+          const int l = K::slot(k, pl);
           int lbl = 0;
           if (p.label) lbl = group_argmax<CL, LPP>(x[k], nvalid, class0);
           if (sub == 0 && l < npix) emit_pixel(p, acc, conf[k], lbl, tile_pix0, off, l, in_img);
@@ -141,12 +187,7 @@ __global__ void __launch_bounds__(kBlockThreads, Cfg<E, C, (MEASURE == kMulti)>:
       for (int t = 0; t < p.T; ++t) {
         float x[PPT][CL];
         if (t > 0) mbar_wait(&full[s], ph);
-        const unsigned char* st = stage_base + static_cast<size_t>(s) * K::STAGE_BYTES + run_off;
-#pragma unroll
-        for (int k = 0; k < PPT; ++k) {
-          if constexpr (K::EXACT) load_run<E, CL, K::VB>(st + k * (G * C * ES), x[k]);
-          else load_run_partial<E, CL>(st + k * (G * C * ES), x[k], nvalid);
-        }
+        load_tile_pixels<K, E, C>(stage_base + static_cast<size_t>(s) * K::STAGE_BYTES, pl, class0, nvalid, x);
         __syncwarp();
         if (lane == 0) mbar_arrive(&empty[s]);
         if (++s == nstage) { s = 0; ph ^= 1u; }
@@ -159,7 +200,7 @@ __global__ void __launch_bounds__(kBlockThreads, Cfg<E, C, (MEASURE == kMulti)>:
       }
 #pragma unroll
       for (int k = 0; k < PPT; ++k) {
-        const int l = k * G + pl;
+        const int l = K::slot(k, pl);
         const float conf = conf_multi<CL, LPP, K::EXACT>(mu[k], m2s[k], nvalid, p);
         if (plain) {
           if (sub == 0) acc.add(conf, p.fx_scale);
@@ -170,6 +211,7 @@ __global__ void __launch_bounds__(kBlockThreads, Cfg<E, C, (MEASURE == kMulti)>:
     }
   }
   acc.flush(p);
+  if (p.fin_n > 0) fused_finalize(p, &s_last);
 }
 
 // ---- generic fallback: any C, any alignment (direct global loads, one thread per pixel) -----
@@ -274,37 +316,12 @@ __global__ void __launch_bounds__(kGenericThreads) score_generic_kernel(const Sc
   flush();
 }
 
-// ---- finalize: fixed point -> f64 mean (:261-263), f32 scatter by example index (:700) -------
-__global__ void finalize_kernel(long long* __restrict__ acc, long long acc_stride, unsigned int* __restrict__ flags,
-                                unsigned long long* __restrict__ tile_counter, int n, double inv_scale_p,
-                                double* __restrict__ scores64, float* __restrict__ pool32,
-                                const long long* __restrict__ example_index, long long num_examples) {
-  pdl_launch_dependents();
-  pdl_wait();  // the scoring kernel's sums are complete and visible
-  const int i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i == 0) *tile_counter = 0ull;  // ready for the next scoring launch on this stream
-  if (i >= n) return;
-  long long total = 0;
-#pragma unroll 8
-  for (int r = 0; r < kAccReplicas; ++r) {
-    total += acc[r * acc_stride + i];
-    acc[r * acc_stride + i] = 0;
-  }
-  const double s = flags[i] ? __longlong_as_double(0x7ff8000000000000ll) : static_cast<double>(total) * inv_scale_p;
-  flags[i] = 0;
-  if (scores64) scores64[i] = s;
-  if (pool32) {
-    const long long e = example_index ? example_index[i] : i;
-    if (e >= 0 && e < num_examples) pool32[e] = static_cast<float>(s);  // f64 -> f32 round-to-nearest
-  }
-}
-
 cudaError_t launch_finalize(long long* acc, long long acc_stride, unsigned int* flags, unsigned long long* tile_counter,
                             int n, double inv_scale_p, double* scores64,
-                            float* pool32, const long long* example_index, long long num_examples,
+                            float* pool32, const long long* example_index, long long index_base, long long num_examples,
                             cudaStream_t stream) {
   if (n <= 0) return cudaSuccess;
-  void* args[] = {&acc, &acc_stride, &flags, &tile_counter, &n, &inv_scale_p, &scores64, &pool32, &example_index, &num_examples};
+  void* args[] = {&acc, &acc_stride, &flags, &tile_counter, &n, &inv_scale_p, &scores64, &pool32, &example_index, &index_base, &num_examples};
   return launch_pdl((const void*)finalize_kernel, dim3((n + 255) / 256), dim3(256), args, 0, stream);
 }
 
@@ -335,6 +352,28 @@ static bool pick(int measure, int T, LaunchPlan& plan) {
   return true;
 }
 
+// Resident CTAs per SM of a tiled kernel at its shared-memory size; the opt-in attribute and the occupancy query are
+// driver calls (~10 us together), so they are made once per (kernel, size, device) and remembered -- a batch-of-8 call is
+// only ~50 us of GPU time and a single-chunk pool pass pays every host microsecond in front of its one launch.
+int resident_ctas(const void* func, int block, int smem_bytes) {
+  struct Entry { const void* func; int smem, dev, per_sm; };
+  static std::mutex mu;
+  static std::vector<Entry> cache;
+  int dev = 0;
+  cudaGetDevice(&dev);
+  std::lock_guard<std::mutex> lock(mu);
+  for (const Entry& e : cache)
+    if (e.func == func && e.smem == smem_bytes && e.dev == dev) return e.per_sm;
+  int per_sm = 0;
+  if (cudaFuncSetAttribute(func, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes) != cudaSuccess ||
+      cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, func, block, smem_bytes) != cudaSuccess || per_sm < 1) {
+    (void)cudaGetLastError();
+    per_sm = 1;
+  }
+  cache.push_back({func, smem_bytes, dev, per_sm});
+  return per_sm;
+}
+
 LaunchPlan plan_score(int dtype, int C, int measure, int T, long long total_pixels, bool aligned, int num_sms,
                       int max_smem_per_block) {
   LaunchPlan plan{};
@@ -356,7 +395,7 @@ LaunchPlan plan_score(int dtype, int C, int measure, int T, long long total_pixe
     int per_cta = (228 * 1024) / plan.ctas_per_sm - 1024;
     if (const char* env = getenv("ALS_SMEM_KB")) per_cta = atoi(env) * 1024;  // tuning knob (bench only)
     if (per_cta > max_smem_per_block) per_cta = max_smem_per_block;
-    const int budget = per_cta - kSmemHeader;
+    const int budget = per_cta - kSmemHeader - 128;  // 128: static shared memory (fused-finalize flag)
     int stages = budget / stage_bytes;
     if (stages > kMaxStages) stages = kMaxStages;
     if (stages >= 2) {
@@ -365,13 +404,7 @@ LaunchPlan plan_score(int dtype, int C, int measure, int T, long long total_pixe
       plan.smem_bytes = kSmemHeader + stages * stage_bytes;
       plan.block = kBlockThreads;
       const long long tiles = (total_pixels + plan.tile_pixels - 1) / plan.tile_pixels;
-      int per_sm = 0;
-      if (cudaFuncSetAttribute(plan.func, cudaFuncAttributeMaxDynamicSharedMemorySize, plan.smem_bytes) != cudaSuccess ||
-          cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, plan.func, plan.block, plan.smem_bytes) != cudaSuccess ||
-          per_sm < 1) {
-        (void)cudaGetLastError();
-        per_sm = 1;
-      }
+      const int per_sm = resident_ctas(plan.func, plan.block, plan.smem_bytes);
       const long long resident = static_cast<long long>(per_sm) * num_sms;  // persistent: one wave
       plan.grid = static_cast<int>(tiles < resident ? (tiles > 0 ? tiles : 1) : resident);
       return plan;
@@ -403,6 +436,7 @@ cudaError_t launch_score(const LaunchPlan& plan, int dtype, ScoreParams p, cudaS
     void* args[] = {&p};
     return launch_pdl(plan.func, dim3(plan.grid), dim3(plan.block), args, plan.smem_bytes, stream);
   }
+  if (p.fin_n > 0) return cudaErrorInvalidValue;  // only the tiled kernel folds the finalize in (callers check plan.tiled)
   const void* f = dtype == 0 ? (const void*)score_generic_kernel<float> : (const void*)score_generic_kernel<__nv_bfloat16>;
   if (plan.smem_bytes > 48 * 1024) {
     err = cudaFuncSetAttribute(f, cudaFuncAttributeMaxDynamicSharedMemorySize, plan.smem_bytes);

@@ -29,7 +29,21 @@ struct ScoreParams {
   float* conf_map;       // optional [N*P]
   uint8_t* label;        // optional [N*P]
   uint8_t* mask;         // optional [N*P]
+  // Fused finalize (tiled kernel only, fin_n > 0): the last CTA to finish turns the fixed-point sums into scores
+  // itself instead of a second launch -- see fused_finalize() in score.cu.  Same fields as launch_finalize.
+  int fin_n;                      // images of this launch, 0 = a separate finalize_kernel follows
+  unsigned int* done_counter;     // CTAs finished so far (zero on entry; the last CTA re-zeroes it)
+  double fin_inv_scale_p;
+  double* fin_scores64;
+  float* fin_pool32;
+  const long long* fin_example_index;
+  long long fin_index_base;
+  long long fin_num_examples;
 };
+
+// Largest launch (images) whose finalize is folded into the scoring kernel's last CTA; above it the separate,
+// fully parallel finalize_kernel is cheaper than one CTA walking 32 accumulator replicas per image.
+constexpr int kFusedFinalizeMaxImages = 2048;
 
 struct LaunchPlan {
   const void* func;   // nullptr -> generic fallback
@@ -44,10 +58,14 @@ LaunchPlan plan_score(int dtype, int C, int measure, int T, long long total_pixe
 
 cudaError_t launch_score(const LaunchPlan& plan, int dtype, ScoreParams p, cudaStream_t stream);
 
-// scores64[i] = flags ? NaN : acc * 2^-shift / P ; optional f32 scatter; re-zeroes acc/flags.
+// Resident CTAs per SM of `func` with `smem_bytes` of dynamic shared memory (sets the opt-in attribute); cached.
+int resident_ctas(const void* func, int block, int smem_bytes);
+
+// scores64[i] = flags ? NaN : acc * 2^-shift / P ; optional f32 scatter pool32[example_index[i]] (example_index == nullptr:
+// pool32[index_base + i]); re-zeroes acc/flags.
 cudaError_t launch_finalize(long long* acc, long long acc_stride, unsigned int* flags, unsigned long long* tile_counter,
                             int n, double inv_scale_p,
-                            double* scores64, float* pool32, const long long* example_index, long long num_examples,
-                            cudaStream_t stream);
+                            double* scores64, float* pool32, const long long* example_index, long long index_base,
+                            long long num_examples, cudaStream_t stream);
 
 }  // namespace als

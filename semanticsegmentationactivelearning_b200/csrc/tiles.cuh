@@ -48,6 +48,15 @@ struct Cfg {
   // (more warps hide the dependent MUFU/FMA chains), else 2
   static constexpr int MINB = (PPT * CL <= 24) ? 3 : 2;
   static_assert((LPP - 1) * CL < C, "every lane must own at least one class");
+  // bf16 logits with an odd class count: a pixel is C*2 bytes, so only every other pixel starts on a 4-byte boundary
+  // and a thread that owns ONE pixel per slot row is left with 2-byte loads (C LDS.U16 per pixel, half of them bank
+  // conflicted: ncu counted 47 % extra shared-memory wavefronts on cfg3 bf16).  PAIR: a thread owns two ADJACENT pixels
+  // (2*C bf16 = C aligned 32-bit words, lane stride C words: odd, conflict free) -- half the load instructions.
+  static constexpr bool PAIR = (ES == 2) && (LPP == 1) && (C % 2 == 1) && (PPT % 2 == 0);
+  // pixel slot inside the tile of the k-th pixel of consumer thread `pl`
+  __host__ __device__ static constexpr int slot(int k, int pl) {
+    return PAIR ? ((k >> 1) * 2 * G + 2 * pl + (k & 1)) : (k * G + pl);
+  }
 };
 
 // ---- shared memory -> registers -------------------------------------------------------
@@ -114,6 +123,51 @@ __device__ __forceinline__ void load_run_partial(const unsigned char* __restrict
       else v = __uint_as_float(static_cast<uint32_t>(*reinterpret_cast<const uint16_t*>(src + 2 * j)) << 16);
     }
     x[j] = v;
+  }
+}
+
+// "Last CTA" ticket for the consumer threads of a tiled kernel (the producer warp has returned): every CTA counts itself
+// done once all its consumer warps have passed this point; returns true in the CTA that finds itself last -- all other
+// CTAs' global writes and atomics are then visible to it (fence, atomic ticket, fence).  Named barrier 1.
+__device__ __forceinline__ bool last_cta_ticket(unsigned int* done_counter, int* s_flag) {
+  __threadfence();
+  asm volatile("bar.sync 1, %0;" ::"n"(kConsumerThreads) : "memory");
+  if (threadIdx.x == 0) {
+    __threadfence();
+    *s_flag = (atomicAdd(done_counter, 1u) == gridDim.x - 1) ? 1 : 0;
+  }
+  asm volatile("bar.sync 1, %0;" ::"n"(kConsumerThreads) : "memory");
+  if (!*s_flag) return false;
+  __threadfence();
+  return true;
+}
+
+// All PPT pixels of consumer thread (pl, class run class0) of one staged tile -> registers.
+template <typename K, typename E, int C>
+__device__ __forceinline__ void load_tile_pixels(const unsigned char* __restrict__ stage, int pl, int class0, int nvalid,
+                                                 float (&x)[K::PPT][K::CL]) {
+  constexpr int CL = K::CL, G = K::G, ES = K::ES, PPT = K::PPT;
+  if constexpr (K::PAIR) {
+#pragma unroll
+    for (int q = 0; q < PPT / 2; ++q) {
+      const uint32_t* src = reinterpret_cast<const uint32_t*>(stage + (q * 2 * G + 2 * pl) * (C * ES));
+      uint32_t w[C];  // 2*C bf16 = C words: pixel 2q is elements 0..C-1, pixel 2q+1 elements C..2C-1
+#pragma unroll
+      for (int i = 0; i < C; ++i) w[i] = src[i];
+#pragma unroll
+      for (int j = 0; j < C; ++j) {
+        x[2 * q][j] = __uint_as_float((j & 1) ? (w[j >> 1] & 0xffff0000u) : (w[j >> 1] << 16));
+        const int e = C + j;
+        x[2 * q + 1][j] = __uint_as_float((e & 1) ? (w[e >> 1] & 0xffff0000u) : (w[e >> 1] << 16));
+      }
+    }
+  } else {
+    const unsigned char* st = stage + (pl * C + class0) * ES;
+#pragma unroll
+    for (int k = 0; k < PPT; ++k) {
+      if constexpr (K::EXACT) load_run<E, CL, K::VB>(st + k * (G * C * ES), x[k]);
+      else load_run_partial<E, CL>(st + k * (G * C * ES), x[k], nvalid);
+    }
   }
 }
 

@@ -121,7 +121,7 @@ def test_cfg2_other_measures_on_mc_mean(torch, scorer):
 
 def test_full_pool_selection_2975(torch, scorer):
     """One full pool pass (2975 images @512x1024, C=19, entropy, chunks of 175 like bench.py): the GPU's score vector
-    fed to the oracle's selection (:705-714) gives the same sorted id set; scores are distinct and finite."""
+    fed to the oracle's selection (:705-714) gives the same sorted id set; scores are finite and (nearly all) distinct."""
     from oracle import reference_np as R
     N, H, W, C, chunk = 2975, 512, 1024, 19, 175
     rng = np.random.default_rng(20191013)
@@ -138,11 +138,11 @@ def test_full_pool_selection_2975(torch, scorer):
         torch.cuda.synchronize()
     ids, u = scorer.pool_select(unl, K)
     scores32 = scorer.pool_scores(N)
-    assert np.all(np.isfinite(scores32)) and len(np.unique(scores32)) == N
+    assert np.all(np.isfinite(scores32)) and len(np.unique(scores32)) >= N - 16      # float32 scores: a few coincide
     assert np.array_equal(u, scores32[unl])
     want_ids, want_u = R.select_lowest(scores32, unl, K)
     assert np.array_equal(want_u, u)
-    assert sorted(ids.tolist()) == sorted(want_ids.tolist())
+    _assert_same_ids(ids, want_ids, scores32, "2975-image pass")
     # and the deterministic completion: ascending (score, id)
     tot_ids, _ = R.select_lowest_total_order(scores32, unl, K)
     assert np.array_equal(ids, tot_ids)

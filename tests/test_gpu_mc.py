@@ -55,8 +55,16 @@ def test_streamed_equals_resident_and_oracle(torch, scorer, shape, dtype):
         for t in range(T):
             scorer.mc_add_sample(xt[t])
         out = scorer.mc_finish(measure, threshold=0.5, want_maps=True)
-        for key in ("pseudo_confidence", "pseudo_mean_confidence", "pseudo_label", "pseudo_mask"):
-            assert torch.equal(out[key], resident[key]), "%s: streamed %s differs from the resident path" % (measure, key)
+        # bit-identical whenever both paths run the same arithmetic.  A stack whose sample planes are not 16-byte
+        # aligned (odd N*H*W*C) sends the RESIDENT call to the generic kernel (classic Welford form), while the streamed
+        # call copies each misaligned sample into an aligned buffer and keeps the tiled kernels: then only the tolerance
+        # against the oracle below applies.
+        es = 2 if dtype == "bfloat16" else 4
+        if (N * H * W * C * es) % 16 == 0:
+            for key in ("pseudo_confidence", "pseudo_mean_confidence", "pseudo_label", "pseudo_mask"):
+                assert torch.equal(out[key], resident[key]), "%s: streamed %s differs from the resident path" % (measure, key)
+        else:
+            assert torch.equal(out["pseudo_label"], resident["pseudo_label"])
         want = R.pixel_confidence(xf, measure)
         got = out["pseudo_confidence"].cpu().numpy()
         assert np.all(np.abs(got - want) <= RTOL * np.abs(want) + ATOL_PIX), measure
@@ -65,7 +73,7 @@ def test_streamed_equals_resident_and_oracle(torch, scorer, shape, dtype):
         scorer.mc_begin((N, H, W, C), dtype)
         for t in range(T):
             scorer.mc_add_sample(xt[t])
-        assert torch.equal(scorer.mc_finish(measure), resident["pseudo_mean_confidence"])
+        assert torch.equal(scorer.mc_finish(measure), out["pseudo_mean_confidence"])
 
 
 def test_streamed_host_samples_and_pool_scatter(torch, scorer):
@@ -88,7 +96,7 @@ def test_streamed_host_samples_and_pool_scatter(torch, scorer):
     assert set(ids.tolist()) <= set(np.setdiff1d(np.arange(12), idx).tolist())     # unvisited 0.0 first (:685)
 
 
-def test_streamed_misaligned_samples_take_the_generic_layout(torch, scorer):
+def test_streamed_misaligned_samples(torch, scorer):
     from oracle import reference_np as R, synth
     T, N, H, W, C = 3, 2, 5, 7, 19
     x = synth.synth_logits(T, 0, N, H, W, C)
