@@ -51,6 +51,23 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
   }
 }
 
+// Release of a TMA-filled shared-memory stage by a warp that has READ it with ordinary ld.shared: the arrive must not be
+// performed before those loads have actually read shared memory, or the producer's next bulk copy can overwrite bytes
+// that are still to be read (write-after-read across the generic and the async proxy).  Nothing in the instruction
+// stream orders them by itself: LDS results are tracked by the scoreboard, SYNCS.ARRIVE reads no loaded register, so it
+// can be issued -- and performed -- while the loads sit in the memory pipeline.  Seen for real in mc.cu (state LDGs
+// queued in front of the LDS: a handful of pixels of one tile per ~10 launches read the NEXT tile's logits).  The cure is
+// a true register dependency: `dep` is derived from every loaded register (callers pass bits >> 1, so it is never
+// 0xffffffff) and predicates the arrive, which therefore waits for the loads' scoreboard.
+__device__ __forceinline__ void mbar_arrive_after_loads(uint64_t* bar, uint32_t dep) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.u32 p, %1, 0xffffffff;\n\t"
+      "@p mbarrier.arrive.shared::cta.b64 _, [%0];\n\t}"
+      ::"r"(smem_u32(bar)), "r"(dep)
+      : "memory");
+}
+
 // For waits that are expected to be long: back off between polls so that the spinning warp does not take
 // issue slots from the warps doing the work (the SM's arbiter favours higher warp ids).
 __device__ __forceinline__ void mbar_wait_relaxed(uint64_t* bar, uint32_t parity) {

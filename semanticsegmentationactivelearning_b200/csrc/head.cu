@@ -479,8 +479,12 @@ score_head_kernel(const HeadParams p, const __grid_constant__ CUtensorMap feat_m
           own[c] = *reinterpret_cast<const float4*>(own_p + ((c ^ own_x) << 4));
           left[c] = *reinterpret_cast<const float4*>(left_p + ((c ^ left_x) << 4));
         }
+        // release the raw slot only once the loads have READ it (common.cuh: mbar_arrive_after_loads)
+        uint32_t dep = 0;
+#pragma unroll
+        for (int c = 0; c < 4; ++c) dep |= __float_as_uint(own[c].x) | __float_as_uint(left[c].x);
         __syncwarp();
-        if (lane == 0) mbar_arrive(&empty_raw[s_row]);  // release: the loads above are ordered before it
+        if (lane == 0) mbar_arrive_after_loads(&empty_raw[s_row], dep >> 1);
         // split in registers while the tensor-memory slot may still be in use, then only the stores wait for it
         uint32_t hi_o[16], lo_o[16], hi_l[16], lo_l[16];
         split_hi_lo(own, hi_o, lo_o);

@@ -87,6 +87,15 @@ __global__ void __launch_bounds__(kBlockThreads, Cfg<E, C, true>::MINB) mc_updat
     const int npix = meta[s].npix;
     float* __restrict__ stp = state + (tile_pix0 / K::TILE_PIX) * L::TILE_FLOATS + tid;
 
+    // logits first, and the stage goes back as soon as they are in registers; only then the state loads: queued in
+    // front of the shared-memory reads they would hold those back for a global-memory latency
+    float x[PPT][CL];
+    load_tile_pixels<K, E, C>(stage_base + static_cast<size_t>(s) * K::STAGE_BYTES, pl, class0, nvalid, x);
+    const uint32_t dep = loaded_dep<PPT, CL>(x);
+    __syncwarp();
+    if (lane == 0) mbar_arrive_after_loads(&empty[s], dep);
+    if (++s == nstage) { s = 0; ph ^= 1u; }
+
     float nmu[PPT][CL];
     float m2s[PPT];
     if constexpr (!FIRST) {
@@ -104,11 +113,6 @@ __global__ void __launch_bounds__(kBlockThreads, Cfg<E, C, true>::MINB) mc_updat
         for (int j = 0; j < CL; ++j) nmu[k][j] = 0.f;
       }
     }
-    float x[PPT][CL];
-    load_tile_pixels<K, E, C>(stage_base + static_cast<size_t>(s) * K::STAGE_BYTES, pl, class0, nvalid, x);
-    __syncwarp();
-    if (lane == 0) mbar_arrive(&empty[s]);
-    if (++s == nstage) { s = 0; ph ^= 1u; }
 
 #pragma unroll
     for (int k = 0; k < PPT; ++k) {

@@ -53,6 +53,19 @@ __device__ __forceinline__ int group_argmax(const float (&x)[CL], int nvalid, in
   return bi;
 }
 
+// Same result for a pixel held by ONE thread (LPP == 1), two instructions per class instead of three: the maximum by
+// the same fmaxf chain conf_single() runs (the compiler shares it), then the FIRST class that equals it.
+template <int CL>
+__device__ __forceinline__ int argmax_first(const float (&x)[CL]) {
+  float m = x[0];
+#pragma unroll
+  for (int j = 1; j < CL; ++j) m = fmaxf(m, x[j]);
+  int bi = 0;
+#pragma unroll
+  for (int j = CL - 1; j >= 0; --j) bi = (x[j] == m) ? j : bi;
+  return (x[0] != x[0]) ? 0 : bi;  // a NaN in class 0 wins like in group_argmax (and np.argmax); the score is NaN anyway
+}
+
 // T == 1: confidence of one pixel straight from its logits.
 //   softmax (:239): e = exp(x - max), p = e / S       -- never materialised
 //   entropy (:243-251): -sum p log p = log S - (sum e*(x-max)) / S   (one log per pixel, not C)
@@ -291,6 +304,15 @@ struct ImageAcc {
     nan = 0;
   }
 };
+
+// Per-pixel outputs of a pixel of a FULL tile that lies inside one image (every tile but ~1 per image): no range or
+// image-boundary checks, the sum goes through ImageAcc::add like on the ranked path.
+__device__ __forceinline__ void emit_pixel_full(const ScoreParams& p, ImageAcc& acc, float conf, int lbl, long long g) {
+  acc.add(conf, p.fx_scale);
+  if (p.conf_map) p.conf_map[g] = conf;
+  if (p.mask) p.mask[g] = (conf < p.threshold) ? 0 : 1;  // :265-269
+  if (p.label) p.label[g] = static_cast<uint8_t>(lbl);
+}
 
 // l: pixel slot in the tile; in_img: slots below it belong to the tile's first image (acc.img).
 __device__ __forceinline__ void emit_pixel(const ScoreParams& p, ImageAcc& acc, float conf, int lbl,

@@ -143,8 +143,9 @@ __global__ void __launch_bounds__(kBlockThreads, Cfg<E, C, (MEASURE == kMulti)>:
       // Pixel slots past the end of the pool (last tile only) hold stale but in-bounds bytes:
       // they are computed like the rest (no divergence around the shuffles) and dropped at emit.
       load_tile_pixels<K, E, C>(stage_base + static_cast<size_t>(s) * K::STAGE_BYTES, pl, class0, nvalid, x);
+      const uint32_t dep = loaded_dep<PPT, CL>(x);
       __syncwarp();
-      if (lane == 0) mbar_arrive(&empty[s]);  // values are in registers: hand the stage back
+      if (lane == 0) mbar_arrive_after_loads(&empty[s], dep);  // values are in registers: hand the stage back
       if (++s == nstage) { s = 0; ph ^= 1u; }
       float conf[PPT];
       bool bad = false;
@@ -163,6 +164,16 @@ __global__ void __launch_bounds__(kBlockThreads, Cfg<E, C, (MEASURE == kMulti)>:
         if (sub == 0) {
 #pragma unroll
           for (int k = 0; k < PPT; ++k) acc.add(conf[k], p.fx_scale);
+        }
+      } else if (in_img == K::TILE_PIX) {  // per-pixel outputs, full tile inside one image
+#pragma unroll
+        for (int k = 0; k < PPT; ++k) {
+          int lbl = 0;
+          if (p.label) {
+            if constexpr (LPP == 1) lbl = argmax_first<CL>(x[k]);
+            else lbl = group_argmax<CL, LPP>(x[k], nvalid, class0);
+          }
+          if (sub == 0) emit_pixel_full(p, acc, conf[k], lbl, tile_pix0 + K::slot(k, pl));
         }
       } else {
 #pragma unroll
@@ -188,8 +199,9 @@ __global__ void __launch_bounds__(kBlockThreads, Cfg<E, C, (MEASURE == kMulti)>:
         float x[PPT][CL];
         if (t > 0) mbar_wait(&full[s], ph);
         load_tile_pixels<K, E, C>(stage_base + static_cast<size_t>(s) * K::STAGE_BYTES, pl, class0, nvalid, x);
+        const uint32_t dep = loaded_dep<PPT, CL>(x);
         __syncwarp();
-        if (lane == 0) mbar_arrive(&empty[s]);
+        if (lane == 0) mbar_arrive_after_loads(&empty[s], dep);
         if (++s == nstage) { s = 0; ph ^= 1u; }
         const float inv_t = __frcp_rn(static_cast<float>(t + 1));
 #pragma unroll

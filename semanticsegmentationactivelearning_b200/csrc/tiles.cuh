@@ -171,6 +171,22 @@ __device__ __forceinline__ void load_tile_pixels(const unsigned char* __restrict
   }
 }
 
+// A word that depends on every register load_tile_pixels() filled (see mbar_arrive_after_loads): the per-pixel class
+// maximum -- the first thing every measure computes anyway, so the chain is shared with it -- OR-ed over the thread's
+// pixels, shifted right so that it can never be all ones.
+template <int PPT, int CL>
+__device__ __forceinline__ uint32_t loaded_dep(const float (&x)[PPT][CL]) {
+  uint32_t d = 0;
+#pragma unroll
+  for (int k = 0; k < PPT; ++k) {
+    float m = x[k][0];
+#pragma unroll
+    for (int j = 1; j < CL; ++j) m = fmaxf(m, x[k][j]);
+    d |= __float_as_uint(m);
+  }
+  return d >> 1;
+}
+
 // ---- the tiled kernel ------------------------------------------------------------------------
 // Per-stage tile descriptor the producer publishes next to the data (sample 0 of a tile only).
 struct TileMeta {
