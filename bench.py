@@ -354,6 +354,7 @@ def main():
     map_outs = {}
 
     one_call = (world == 1 and len(chunks) == 1 and not head and not maps and not streamed)
+    sel_pairs = []
     lib_ms = []
     if one_call:
         sc.enable_timing(True)
@@ -391,7 +392,14 @@ def main():
         if maps:
             return None, None                  # the training-path call site has no selection (:229-275)
         # :705-715; N > 1: local candidates -> one ncclAllGather -> merge, all on the device, one D2H
-        return sc.pool_select_global(unl_global, K_SELECT, (id0, id0 + N), N)
+        if record:
+            s0, s1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            s0.record()
+        out = sc.pool_select_global(unl_global, K_SELECT, (id0, id0 + N), N)
+        if record:
+            s1.record()
+            sel_pairs.append((s0, s1))
+        return out
 
     def barrier():
         if world > 1:
@@ -456,6 +464,23 @@ def main():
     peak, peak_src = load_peaks()
     achieved = bytes_launch / (avg_ms * 1e-3) / 1e9
     kernel_share = (sum(m for m, _ in lib_ms) if one_call else sum(a.elapsed_time(b) for a, b, _ in ev_pairs)) / ms_total
+
+    # ---- per-rank view (N > 1): a step ends with a collective, so it lasts as long as the SLOWEST rank's scoring plus the
+    # exchange; rank 0's kernel share therefore also contains its wait for slower GPUs (they differ by 1-2 % under the
+    # power cap).  Report every rank's own scoring time and its time in the selection call (wait + exchange + merge).
+    per_rank = None
+    if world > 1:
+        mine = torch.tensor([sum(a.elapsed_time(b) for a, b, _ in ev_pairs) / args.steps,
+                             (sum(a.elapsed_time(b) for a, b in sel_pairs) / max(len(sel_pairs), 1))], device=dev)
+        allr = torch.empty(world * 2, device=dev)
+        dist.all_gather_into_tensor(allr, mine)
+        allr = allr.view(world, 2).cpu().numpy()
+        per_rank = {"scoring_ms_per_step": [round(float(v), 3) for v in allr[:, 0]],
+                    "select_call_ms": [round(float(v), 3) for v in allr[:, 1]],
+                    "slowest_rank_scoring_share_of_step": float(allr[:, 0].max() / ms_step),
+                    "exchange_ms_on_slowest_rank": float(allr[int(allr[:, 0].argmax()), 1]),
+                    "note": "select_call_ms on a fast rank includes waiting for the slowest rank at the all-gather; on the "
+                            "slowest rank it is the cost of the exchange itself (candidates + one ncclAllGather + merge + results)"}
 
     # ---- diagnostic: the scoring kernel alone, launched back to back on one chunk (host latency hidden) ----
     burst_buf = chunks[0][0]
@@ -585,7 +610,7 @@ def main():
                          "traffic_source": "profiles/ncu_traffic.json (dram__bytes_read+write of one ncu --set full launch)",
                          "peak_source": peak_src, "kernel": desc["kernel"],
                          "bytes_per_launch": bytes_launch, "avg_launch_ms": avg_ms, "launches_timed": len(full),
-                         "kernel_share_of_step": kernel_share, "kernel_burst": burst},
+                         "kernel_share_of_step": kernel_share, "per_rank": per_rank, "kernel_burst": burst},
             "cpu_baseline": cpu,
             "selected_ids_head": [int(i) for i in ids[:5]] if ids is not None else None,
             "ids_check": ids_check, "cpu_affinity": affinity,

@@ -23,4 +23,25 @@ with Scorer(0) as sc:
                       dtype=dtype)
         torch.cuda.synchronize()
         assert np.allclose(hs, out["pseudo_mean_confidence"].cpu().numpy(), rtol=0, atol=0), (hs, out)
+    # round 2: streamed Monte-Carlo accumulation (state in HBM), one-call pool pass, selection with a ragged unlabelled
+    # set and k > 1024 (second ranking kernel), fused classifier head on an odd-sized feature map, world-1 NCCL exchange
+    x = sc.synth_logits(3, 0, 4, 33, 31, 19)
+    sc.mc_begin((4, 33, 31, 19))
+    for t in range(3):
+        sc.mc_add_sample(x[t].contiguous())
+    s = sc.mc_finish("variance", batch_indices=np.arange(4))
+    torch.cuda.synchronize()
+    ids, u = sc.rank_pool(x, np.array([3, 0, 2]), 2, "variance")
+    sc.pool_begin(3000)
+    ids, u = sc.pool_select(np.arange(0, 3000, 2), 1400)
+    assert len(ids) == 1400
+    rng = np.random.default_rng(0)
+    feat = torch.from_numpy(rng.standard_normal((2, 9, 131, 16)).astype(np.float32)).cuda()
+    sc.prepare_head((0.4 * rng.standard_normal((3, 3, 19, 16))).astype(np.float32))
+    sc.score_features(feat, "entropy")
+    sc.score_features(torch.stack([feat, 0.9 * feat]), "variance")
+    Scorer.comm_init_all([sc])
+    sc.pool_begin(8)
+    ids, u = sc.pool_select_global(np.arange(8), 3, (0, 8))
+    torch.cuda.synchronize()
 print("sanitize case ok")

@@ -36,6 +36,7 @@ __device__ __forceinline__ bool pair_less(uint32_t ao, unsigned long long ai, ui
 }
 
 constexpr int kSelThreads = 1024;
+constexpr int kSelItems = 4;  // pairs per thread kept in registers across the radix passes
 
 // pair i of the source; false = not part of this selection (not owned by this rank / padding)
 __device__ __forceinline__ bool load_pair(const SelectSrc& s, long long i, float& key, long long& id) {
@@ -130,13 +131,45 @@ __global__ void __launch_bounds__(kSelThreads) select_kernel(const SelectSrc s, 
   if (out.uconf)
     for (long long i = tid; i < out.uconf_M; i += kSelThreads) out.uconf[i] = out.uconf_pool[out.uconf_ids[i]];
 
-  // ---- how many pairs take part ----
+  // ---- the pairs: up to kSelItems per thread stay in registers for all passes (pools up to 4096 images -- every
+  //      BASELINE configuration); larger inputs are re-read from global memory (L2 resident) in every pass ----
+  const bool cached = M <= static_cast<long long>(kSelItems) * kSelThreads;
+  uint32_t co[kSelItems];
+  unsigned long long cb[kSelItems];
+  float ck[kSelItems];
+  bool cv[kSelItems];
   long long mine = 0;
-  {
+  if (cached) {
+#pragma unroll
+    for (int q = 0; q < kSelItems; ++q) {
+      const long long i = tid + static_cast<long long>(q) * kSelThreads;
+      float key = 0.f;
+      long long id = 0;
+      cv[q] = i < M && load_pair(s, i, key, id);
+      ck[q] = key;
+      co[q] = orderable(key);
+      cb[q] = biased(id);
+      mine += cv[q] ? 1 : 0;
+    }
+  } else {
     float key;
     long long id;
     for (long long i = tid; i < M; i += kSelThreads) mine += load_pair(s, i, key, id) ? 1 : 0;
   }
+  // fn(orderable key, biased id, key) for every pair of this thread that takes part
+  auto visit = [&](auto&& fn) {
+    if (cached) {
+#pragma unroll
+      for (int q = 0; q < kSelItems; ++q)
+        if (cv[q]) fn(co[q], cb[q], ck[q]);
+    } else {
+      for (long long i = tid; i < M; i += kSelThreads) {
+        float key;
+        long long id;
+        if (load_pair(s, i, key, id)) fn(orderable(key), biased(id), key);
+      }
+    }
+  };
   mine = warp_sum_ll(mine);
   if (lane == 0) s_warp[tid >> 5] = mine;
   __syncthreads();
@@ -158,11 +191,7 @@ __global__ void __launch_bounds__(kSelThreads) select_kernel(const SelectSrc s, 
       __syncthreads();
       const uint32_t pord = s_ord;
       const unsigned long long pid = s_id;
-      for (long long i = tid; i < M; i += kSelThreads) {
-        float key;
-        long long id;
-        if (!load_pair(s, i, key, id)) continue;
-        const uint32_t o = orderable(key);
+      visit([&](uint32_t o, unsigned long long b, float) {
         unsigned int digit;
         bool match;
         if (pass < 4) {
@@ -170,14 +199,13 @@ __global__ void __launch_bounds__(kSelThreads) select_kernel(const SelectSrc s, 
           match = (pass == 0) || ((o >> sh) == (pord >> sh));
           digit = (o >> (24 - 8 * pass)) & 0xffu;
         } else {
-          const unsigned long long b = biased(id);
           const int q = pass - 4;
           const int sh = 64 - 8 * q;
           match = (o == pord) && (q == 0 || ((b >> sh) == (pid >> sh)));
           digit = static_cast<unsigned int>((b >> (56 - 8 * q)) & 0xffull);
         }
         if (match) atomicAdd(&hist[digit], 1u);
-      }
+      });
       __syncthreads();
       if (tid < 32) {
         // bin scan: lane l owns bins 8l .. 8l+7; the bin where the running count reaches `remaining` is the digit
@@ -228,26 +256,22 @@ __global__ void __launch_bounds__(kSelThreads) select_kernel(const SelectSrc s, 
   const uint32_t tord = s_ord;
   const unsigned long long tidb = s_id;
   const unsigned int cap = static_cast<unsigned int>(kk);  // unique ids give exactly kk survivors; duplicates must not overflow
-  for (long long i = tid; i < (kk > 0 ? M : 0); i += kSelThreads) {
-    float key;
-    long long id;
-    if (!load_pair(s, i, key, id)) continue;
-    const uint32_t o = orderable(key);
-    const unsigned long long b = biased(id);
-    if (!pair_less(tord, tidb, o, b)) {  // (o, b) <= threshold
-      const unsigned int pos = atomicAdd(&s_count, 1u);
-      if (pos < cap) {
-        if (sort_here) {
-          so[pos] = o;
-          sb[pos] = b;
-          sk[pos] = key;
-        } else {
-          tmp_keys[pos] = key;
-          tmp_ids[pos] = id;
+  if (kk > 0)
+    visit([&](uint32_t o, unsigned long long b, float key) {
+      if (!pair_less(tord, tidb, o, b)) {  // (o, b) <= threshold
+        const unsigned int pos = atomicAdd(&s_count, 1u);
+        if (pos < cap) {
+          if (sort_here) {
+            so[pos] = o;
+            sb[pos] = b;
+            sk[pos] = key;
+          } else {
+            tmp_keys[pos] = key;
+            tmp_ids[pos] = static_cast<long long>(b ^ 0x8000000000000000ull);
+          }
         }
       }
-    }
-  }
+    });
   __syncthreads();
   const long long n = s_count < cap ? s_count : cap;
   if (tid == 0 && out.count) out.count[0] = n;
