@@ -239,6 +239,55 @@ def test_t16_c66_small(torch, scorer):
             assert_scores(out["pseudo_mean_confidence"], R.image_scores(want), f"T16 C66 {dtype} {measure}")
 
 
+def test_outputs_stay_inside_their_buffers(torch, scorer):
+    """compute-sanitizer is closed on this pool (profiles/r02_sanitize_memcheck_refusal.txt), so the write side of memory
+    safety is checked by hand: every output lives in the middle of a sentinel-filled allocation and the guard bands must
+    be untouched after the kernels ran -- odd shapes (ragged last tile, images straddling tiles), every lane layout, the
+    generic kernel, T > 1, bf16, the streamed path and the selection block."""
+    from oracle import synth
+    G = 4096
+
+    def guarded(n, dtype, fill):
+        buf = torch.full((n + 2 * G,), fill, dtype=dtype, device="cuda")
+        return buf, buf[G:G + n]
+
+    def intact(buf, n, fill):
+        return bool((buf[:G] == fill).all() and (buf[G + n:] == fill).all())
+
+    for (T, N, H, W, C, dt) in [(1, 5, 33, 47, 19, "float32"), (1, 3, 17, 23, 6, "bfloat16"), (3, 2, 9, 13, 66, "float32"),
+                                (2, 3, 7, 9, 23, "float32"), (1, 2, 5, 5, 150, "bfloat16"), (4, 3, 31, 33, 19, "bfloat16")]:
+        x = synth.synth_logits(T, 0, N, H, W, C, dtype=dt)
+        xt = torch.from_numpy(x.view(np.int16) if dt == "bfloat16" else x).cuda()
+        if dt == "bfloat16":
+            xt = xt.view(torch.bfloat16)
+        P = N * H * W
+        cb, conf = guarded(P, torch.float32, -7.0)
+        lb, label = guarded(P, torch.uint8, 0xAB)
+        mb, mask = guarded(P, torch.uint8, 0xCD)
+        sb, scores = guarded(N, torch.float64, -3.0)
+        out = {"pseudo_confidence": conf.view(N, H, W), "pseudo_mean_confidence": scores, "pseudo_label": label.view(N, H, W),
+               "pseudo_mask": mask.view(N, H, W)}
+        for measure in MEASURES + (("variance",) if T > 1 else ()):
+            scorer.pseudo_annotation(xt, measure, 0.5, out=out)
+            torch.cuda.synchronize()
+            assert intact(cb, P, -7.0) and intact(lb, P, 0xAB) and intact(mb, P, 0xCD) and intact(sb, N, -3.0), (T, N, H, W, C, dt, measure)
+            assert bool((conf > -1.0).all()) and bool((scores > -1.0).all())          # ... and every element was written
+        if T > 1:
+            scorer.mc_begin((N, H, W, C), dt, label=label.view(N, H, W))
+            for t in range(T):
+                scorer.mc_add_sample(xt[t].contiguous())
+            scorer.mc_finish("variance")
+            torch.cuda.synchronize()
+            assert intact(lb, P, 0xAB)
+    kb, keys = guarded(777, torch.float32, -7.0)
+    ib, ids = guarded(777, torch.int64, -5)
+    keys.copy_(torch.rand(777, device="cuda"))
+    ids.copy_(torch.randperm(777, device="cuda"))
+    ok, oi = scorer.select_smallest(keys, ids, 100)
+    torch.cuda.synchronize()
+    assert intact(kb, 777, -7.0) and intact(ib, 777, -5) and len(oi) == 100
+
+
 def test_pool_select_rejects_duplicates_and_bad_ids(torch, scorer):
     scorer.pool_begin(8)
     with pytest.raises(ValueError):
