@@ -435,8 +435,10 @@ def main():
     if not maps:
         full_scores = sc.pool_scores(world * N)       # after the exchange every rank holds the whole vector
         if rank == 0:
-            from oracle import reference_np as R
-            want_ids, want_u = R.select_lowest(full_scores, unl_global, K_SELECT)     # np.argpartition, :705-714
+            # /root/reference/active_learning.py:705-714 verbatim (NumPy only; the oracle package stays out of this path)
+            want_u = full_scores[unl_global]
+            k_sel = np.minimum(len(unl_global), K_SELECT)
+            want_ids = unl_global[np.argpartition(want_u, k_sel)[:k_sel]]
             # the synthetic pool aliases `resident` distinct images, so scores repeat and the k-th boundary falls inside
             # a group of EQUAL scores, where np.argpartition's choice is arbitrary: compare the selected score multiset
             # and require every id strictly below the k-th score on both sides
@@ -447,7 +449,7 @@ def main():
                          "unlabelled_confidence_match": bool(np.array_equal(conf, want_u)),
                          "scores_finite": bool(np.all(np.isfinite(full_scores))),
                          "distinct_scores": int(len(np.unique(full_scores))),
-                         "how": "oracle/reference_np.select_lowest (np.argpartition, :705-714) on the GPU path's own float32 "
+                         "how": "np.argpartition exactly as active_learning.py:705-714 on the GPU path's own float32 "
                                 "score vector of the last timed pass; equal ids below the k-th score, equal score multiset "
                                 "(ties at the k-th score excused: the synthetic pool aliases its resident images)"}
 

@@ -22,7 +22,10 @@ __host__ __device__ constexpr int ppt_for(int C, int es, bool multi) {
   const int row = (kConsumerThreads / lpp) * C * es;  // bytes per pixel-slot row
   int ppt = 1;
   const int reg_cap = multi ? 20 : 40;
-  while (ppt < 4 && 2 * ppt * cl <= reg_cap && 2 * ppt * row <= 32 * 1024) ppt *= 2;
+#ifndef ALS_PPT_MAX   // bring-up knob: cap on the pixels per thread
+#define ALS_PPT_MAX 4
+#endif
+  while (ppt < ALS_PPT_MAX && 2 * ppt * cl <= reg_cap && 2 * ppt * row <= 32 * 1024) ppt *= 2;
   return ppt;
 }
 __host__ __device__ constexpr int pow2_divisor(int v, int cap) {
@@ -46,7 +49,10 @@ struct Cfg {
   static constexpr int VB = EXACT ? pow2_divisor(gcd_i(CL * ES, C * ES), 16) : ES;
   // resident CTAs per SM the kernel is compiled for: 3 when the per-thread class registers are few
   // (more warps hide the dependent MUFU/FMA chains), else 2
-  static constexpr int MINB = (PPT * CL <= 24) ? 3 : 2;
+#ifndef ALS_MINB_SMALL  // bring-up knob: resident CTAs per SM the small-footprint kernels are compiled for
+#define ALS_MINB_SMALL 3
+#endif
+  static constexpr int MINB = (PPT * CL <= 24) ? ALS_MINB_SMALL : 2;
   static_assert((LPP - 1) * CL < C, "every lane must own at least one class");
   // bf16 logits with an odd class count: a pixel is C*2 bytes, so only every other pixel starts on a 4-byte boundary
   // and a thread that owns ONE pixel per slot row is left with 2-byte loads (C LDS.U16 per pixel, half of them bank

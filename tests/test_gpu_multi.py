@@ -77,6 +77,20 @@ def test_single_process_all_gpus(torch):
         for r, sc in enumerate(scorers):
             with torch.cuda.device(r):
                 np.testing.assert_allclose(sc.pool_scores(N), conf, rtol=RTOL)
+        # a selection larger than the one-launch limit (1024 survivors): second ranking kernel in both phases
+        big = [Scorer(d) for d in range(world)]
+        try:
+            Scorer.comm_init_all(big)
+            NB = 2600 + world
+            bshards = [shard_bounds(NB, r, world) for r in range(world)]
+            for r, sc in enumerate(big):
+                with torch.cuda.device(r):
+                    sc.pool_begin(NB)                     # nothing scored: every confidence is 0.0, ties go to the lower id
+            ids, u = Scorer.pool_select_global_all(big, np.arange(NB)[::-1].copy(), 1500, bshards)
+            assert ids.tolist() == list(range(1500)) and np.all(u == 0)
+        finally:
+            for sc in big:
+                sc.close()
         # shards that do not tile the pool are an error, not a silently short selection
         if world > 1:
             bad = list(shards)
