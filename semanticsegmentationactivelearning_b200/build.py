@@ -11,7 +11,7 @@ PKG = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(PKG, "csrc")
 _TAG = os.environ.get("ALS_BUILD_TAG", "")       # bring-up builds live beside the shipped library (see _lib.py)
 LIB = os.path.join(PKG, "libalscore%s.so" % ("_" + _TAG if _TAG else ""))
-SOURCES = ["score.cu", "mc.cu", "head.cu", "select.cu", "synth.cu", "comm.cu", "capi.cu"]
+SOURCES = ["score.cu", "mc.cu", "head.cu", "select.cu", "synth.cu", "comm.cu", "stage.cu", "capi.cu"]
 HEADERS = ["common.cuh", "pixel_math.cuh", "tiles.cuh", "tc05.cuh", "head.cuh", "score.cuh", "mc.cuh", "select.cuh", "synth.cuh", "ctx.h", os.path.join("..", "..", "include", "alscore.h")]
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
@@ -60,7 +60,7 @@ def build(force: bool = False, verbose: bool = False) -> str:
             list(ex.map(compile_one, jobs))
     objs = [os.path.join(objdir, s.replace(".cu", ".o")) for s in SOURCES]
     if force or jobs or _stale(LIB, objs):
-        cmd = [nvcc, "-shared", "-gencode", "arch=compute_100a,code=sm_100a", "-o", LIB, *objs, "-ldl"]
+        cmd = [nvcc, "-shared", "-gencode", "arch=compute_100a,code=sm_100a", "-o", LIB, *objs, "-ldl", "-lpthread"]
         if verbose:
             print(" ".join(cmd), flush=True)
         r = subprocess.run(cmd, capture_output=True, text=True)

@@ -279,15 +279,15 @@ int stage_chunk(als_ctx* ctx, const unsigned char* host, const Shape& s, int es,
   const size_t img_bytes = static_cast<size_t>(s.P()) * s.C * es;
   // the previous user of this buffer must have been scored
   ALS_CUDA(ctx, cudaStreamWaitEvent(ctx->copy_stream, ctx->ev_scored[b], 0));
+  // (als::stage_copy: pinned sources are one cudaMemcpyAsync, large pageable ones go through the parallel bounce pipeline)
   if (nb == s.N) {
     // the whole batch: [T, nb, P, C] is one dense range on both sides -> one copy instead of T
-    ALS_CUDA(ctx, cudaMemcpyAsync(ctx->stage[b], host, static_cast<size_t>(s.T) * nb * img_bytes, cudaMemcpyHostToDevice,
-                                  ctx->copy_stream));
+    ALS_TRY(als::stage_copy(ctx, ctx->stage[b], host, static_cast<size_t>(s.T) * nb * img_bytes));
   } else {
     for (int64_t t = 0; t < s.T; ++t) {
       const unsigned char* src = host + (static_cast<size_t>(t) * s.N + n0) * img_bytes;
       unsigned char* dst = static_cast<unsigned char*>(ctx->stage[b]) + static_cast<size_t>(t) * nb * img_bytes;
-      ALS_CUDA(ctx, cudaMemcpyAsync(dst, src, static_cast<size_t>(nb) * img_bytes, cudaMemcpyHostToDevice, ctx->copy_stream));
+      ALS_TRY(als::stage_copy(ctx, dst, src, static_cast<size_t>(nb) * img_bytes));
     }
   }
   ALS_CUDA(ctx, cudaEventRecord(ctx->ev_copied[b], ctx->copy_stream));
@@ -378,6 +378,7 @@ int als_ctx_destroy(als_ctx* ctx) {
   if (ctx->stream) cudaStreamSynchronize(ctx->stream);
   if (ctx->copy_stream) cudaStreamSynchronize(ctx->copy_stream);
   if (ctx->scratch_used) cudaEventSynchronize(ctx->ev_scratch);
+  als::stage_destroy(ctx);
   als_comm_destroy(ctx);
   void* ptrs[] = {ctx->acc, ctx->flags, ctx->tile_counter, ctx->scores_dev, ctx->index_dev, ctx->pool32, ctx->sel_ids,
                   ctx->sel_out, ctx->sel_tmp_keys, ctx->sel_tmp_ids, ctx->stage[0], ctx->stage[1], ctx->maps_dev,

@@ -10,6 +10,10 @@
 #include "../../include/alscore.h"
 #include "select.cuh"
 
+namespace als {
+class HostStager;  // stage.cu: parallel staging of pageable host memory
+}
+
 struct als_ctx {
   int device = 0;
   int num_sms = 148;
@@ -60,6 +64,7 @@ struct als_ctx {
   cudaEvent_t ev_copied[2] = {nullptr, nullptr};
   cudaEvent_t ev_scored[2] = {nullptr, nullptr};
   int stage_next = 0;
+  als::HostStager* stager = nullptr;  // created on the first large pageable source
   // per-pixel output staging for the host path
   void* maps_dev = nullptr;
   size_t maps_cap = 0;
@@ -142,6 +147,12 @@ int scratch_begin(als_ctx* ctx, cudaStream_t st);
 int scratch_end(als_ctx* ctx, cudaStream_t st);
 
 int check_device_ptr(als_ctx* ctx, const void* p, const char* what);
+
+// Host -> device copy on the context's copy stream (stage.cu): pinned sources directly, large pageable sources through
+// the parallel bounce-buffer pipeline.  On return the source may be reused only once ev_copied has fired (pinned) --
+// callers record and wait for it as before.
+int stage_copy(als_ctx* ctx, void* dst, const void* src, size_t bytes);
+void stage_destroy(als_ctx* ctx);
 
 // ---- pieces of the :705-715 selection shared by als_pool_select (capi.cu) and the multi-GPU exchange (comm.cu) ----
 int validate_unlabelled(als_ctx* ctx, const int64_t* unlabelled, int64_t M);

@@ -192,6 +192,31 @@ def test_misaligned_and_odd_shapes(torch, scorer):
         assert sorted(ids.tolist()) == sorted(np.argsort(want, kind="stable")[:2].tolist())
 
 
+def test_large_pageable_host_logits(torch, scorer):
+    """Plain NumPy arrays (pageable memory -- what the reference's sess.run hands out, :697-698) above 8 MB go through the
+    parallel bounce-buffer staging (csrc/stage.cu): same bits as the device path, for a whole pool in one call, for a batch
+    that is a slice (T > 1: one copy per sample plane) and with the source buffer reused right after the call returns."""
+    x = scorer.synth_logits(1, 0, 6, 384, 512, 19)                 # 6 x 14.9 MB
+    want = _np(scorer.score(x, "entropy"))
+    host = x.cpu().numpy().copy()
+    assert np.array_equal(scorer.score(host, "entropy"), want)
+    scorer.pool_begin(6)
+    buf = np.empty_like(host[:2])
+    for i in (0, 2, 4):                                            # reuse ONE host buffer: "returns once staged"
+        buf[...] = host[i:i + 2]
+        scorer.pool_score_batch(buf, np.arange(i, i + 2), "entropy")
+        buf[...] = 0
+    assert np.array_equal(scorer.pool_scores(6), want.astype(np.float32))
+    xt = scorer.synth_logits(3, 0, 4, 256, 512, 19)                # T = 3
+    want_t = _np(scorer.score(xt, "variance"))
+    host_t = xt.cpu().numpy().copy()
+    assert np.array_equal(scorer.score(host_t, "variance"), want_t)
+    out = scorer.pseudo_annotation(host, "margin", 0.7)
+    dev = scorer.pseudo_annotation(x, "margin", 0.7)
+    for key in ("pseudo_confidence", "pseudo_label", "pseudo_mask"):
+        assert np.array_equal(out[key], _np(dev[key])), key
+
+
 def test_non_default_stream(torch, scorer):
     """Scoring under `with torch.cuda.stream(side)` is ordered after the producer on that stream, pool_* entries
     follow torch's current stream too, and alternating streams on one context never share the accumulators in flight."""
