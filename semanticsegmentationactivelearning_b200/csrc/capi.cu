@@ -120,6 +120,17 @@ using als::scratch_end;
 
 namespace {
 
+// Fixed-point scale of the per-image sums.  f32 logits: as fine as 63 bits allow (2^44 at most: the quantisation of a
+// confidence is then below 2^-45, far under an f32 half-ulp -- the sum is the exact f64 sum of the f32 map).  bf16
+// logits: 2^22, the grid the FMA-pipe conversion of the hot kernel produces (pixel_math.cuh: ImageAcc::add_q22); with
+// 8-bit inputs and a 1e-2 tolerance nothing is lost, and every bf16 path (tiled, generic, streamed) uses the same grid.
+int ceil_log2_ll(long long v);
+int fx_shift_for(int dtype, long long P) {
+  if (dtype == ALS_BF16) return 22;
+  int shift = 62 - ceil_log2_ll(P);
+  return shift > 44 ? 44 : shift;
+}
+
 int ceil_log2_ll(long long v) {
   int b = 0;
   while ((1ll << b) < v) ++b;
@@ -164,8 +175,7 @@ int score_device(als_ctx* ctx, const void* logits, int dtype, const Shape& s, in
   als::LaunchPlan plan = als::plan_score(dtype, static_cast<int>(s.C), measure, static_cast<int>(s.T), s.N * P, aligned,
                                          ctx->num_sms, ctx->max_smem);
   ALS_TRY(scratch_begin(ctx, stream));
-  int shift = 62 - ceil_log2_ll(P);
-  if (shift > 44) shift = 44;
+  const int shift = fx_shift_for(dtype, P);
   als::ScoreParams p{};
   p.logits = logits;
   p.sample_stride = sample_stride;
@@ -1203,8 +1213,7 @@ int als_mc_finish(als_ctx* ctx, int measure, double* scores, const int64_t* exam
   const als::McPlan plan = als::plan_mc(ctx->mc_dtype, static_cast<int>(s.C), s.N * s.P(), ctx->mc_tiled == 1, ctx->num_sms,
                                         ctx->max_smem);
   const long long P = s.P();
-  int shift = 62 - ceil_log2_ll(P);
-  if (shift > 44) shift = 44;
+  const int shift = fx_shift_for(ctx->mc_dtype, P);
   als::ScoreParams p{};
   p.total_pixels = s.N * P;
   p.P = P;

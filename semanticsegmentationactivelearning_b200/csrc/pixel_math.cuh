@@ -293,6 +293,15 @@ struct ImageAcc {
     sum += __float2ll_rn(conf * fx_scale);
   }
 
+  // bf16 logits (fixed-point scale 2^22, capi.cu: fx_shift_for): the same integer as add() gives -- round-to-nearest-even
+  // of conf * 2^22 -- without the F2I.S64 on the XU pipe: conf + 3 lies in [2, 4] for conf in [-1, 1], where a float's
+  // mantissa IS (conf + 1) * 2^22 on a grid of 2^-22 (3 * 2^22 is even, so the tie rule is the same); one FADD and one
+  // integer add on the FMA / ALU pipes per pixel.  NaN: garbage here, reported through the flag as in add().
+  __device__ __forceinline__ void add_q22(float conf) {
+    nan |= (conf != conf) ? 1u : 0u;
+    sum += static_cast<int>(__float_as_uint(conf + 3.0f) - 0x40400000u);
+  }
+
   __device__ __forceinline__ void flush(const ScoreParams& p) {  // warp-collective
     const long long s = warp_sum_ll(sum);
     const unsigned int n = __any_sync(0xffffffffu, nan != 0);
