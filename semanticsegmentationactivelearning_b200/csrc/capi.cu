@@ -79,13 +79,23 @@ cudaStream_t resolve_stream(als_ctx* ctx, void* stream) {
 }
 
 // The accumulators / flags / tile counter are one set per context: a launch sequence on another stream than the
-// previous one first waits for that one's end-of-sequence event.
+// previous one first waits for everything queued on that stream.  The event is recorded LAZILY, at the switch (it then
+// covers the last launch sequence and whatever else the old stream holds): recording one after every call would put a
+// stream operation between consecutive scoring launches and cost them their programmatic-dependent-launch overlap
+// (measured: 52.0 -> 50 us per batch-of-8 call).  The stream a call ran on must therefore still exist when the next call
+// arrives on a different one; if recording on it fails the context falls back to a device-wide synchronisation.
 int scratch_begin(als_ctx* ctx, cudaStream_t st) {
-  if (ctx->scratch_used && st != ctx->scratch_stream) ALS_CUDA(ctx, cudaStreamWaitEvent(st, ctx->ev_scratch, 0));
+  if (ctx->scratch_used && st != ctx->scratch_stream) {
+    cudaError_t e = cudaEventRecord(ctx->ev_scratch, ctx->scratch_stream);
+    if (e == cudaSuccess) e = cudaStreamWaitEvent(st, ctx->ev_scratch, 0);
+    if (e != cudaSuccess) {
+      (void)cudaGetLastError();
+      ALS_CUDA(ctx, cudaDeviceSynchronize());
+    }
+  }
   return ALS_OK;
 }
 int scratch_end(als_ctx* ctx, cudaStream_t st) {
-  ALS_CUDA(ctx, cudaEventRecord(ctx->ev_scratch, st));
   ctx->scratch_stream = st;
   ctx->scratch_used = true;
   return ALS_OK;
@@ -246,7 +256,10 @@ int ensure_acc(als_ctx* ctx, int64_t n) {
   int64_t cap = ctx->acc_cap > 0 ? ctx->acc_cap : 1024;
   while (cap < n) cap *= 2;
   // the old set may still be in use on whichever stream ran the last launch sequence
-  if (ctx->scratch_used) ALS_CUDA(ctx, cudaEventSynchronize(ctx->ev_scratch));
+  if (ctx->scratch_used && cudaStreamSynchronize(ctx->scratch_stream) != cudaSuccess) {
+    (void)cudaGetLastError();
+    ALS_CUDA(ctx, cudaDeviceSynchronize());
+  }
   ALS_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
   if (ctx->acc) ALS_CUDA(ctx, cudaFree(ctx->acc));
   if (ctx->flags) ALS_CUDA(ctx, cudaFree(ctx->flags));
@@ -387,7 +400,10 @@ int als_ctx_destroy(als_ctx* ctx) {
   DeviceGuard g(ctx->device);
   if (ctx->stream) cudaStreamSynchronize(ctx->stream);
   if (ctx->copy_stream) cudaStreamSynchronize(ctx->copy_stream);
-  if (ctx->scratch_used) cudaEventSynchronize(ctx->ev_scratch);
+  if (ctx->scratch_used && cudaStreamSynchronize(ctx->scratch_stream) != cudaSuccess) {
+    (void)cudaGetLastError();
+    cudaDeviceSynchronize();
+  }
   als::stage_destroy(ctx);
   als_comm_destroy(ctx);
   void* ptrs[] = {ctx->acc, ctx->flags, ctx->tile_counter, ctx->scores_dev, ctx->index_dev, ctx->pool32, ctx->sel_ids,
