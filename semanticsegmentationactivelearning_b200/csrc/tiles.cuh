@@ -21,7 +21,10 @@ __host__ __device__ constexpr int ppt_for(int C, int es, bool multi) {
   const int cl = cdiv(C, lpp);
   const int row = (kConsumerThreads / lpp) * C * es;  // bytes per pixel-slot row
   int ppt = 1;
-  const int reg_cap = multi ? 20 : 40;
+#ifndef ALS_MULTI_REGCAP   // bring-up knob: register budget (class values per thread) of the T > 1 kernels
+#define ALS_MULTI_REGCAP 20
+#endif
+  const int reg_cap = multi ? ALS_MULTI_REGCAP : 40;
 #ifndef ALS_PPT_MAX   // bring-up knob: cap on the pixels per thread
 #define ALS_PPT_MAX 4
 #endif
