@@ -21,8 +21,9 @@
  *     stream"), ALS_STREAM_CTX is the context's stream.  Entries without a `stream` argument (the als_pool_*,
  *     als_mc_* and *_host families) run on the context's stream, see als_ctx_set_stream.
  *   - a context owns ONE set of per-image accumulators.  Calls on different streams are allowed: a call whose stream
- *     differs from the previous call's first waits (on the device) for that call's kernels, so the scratch is never
- *     shared by two launches in flight.  One context per host thread.
+ *     differs from the previous call's first waits (on the device) for the work queued on that stream, so the scratch is
+ *     never shared by two launches in flight; the previous call's stream must still exist at that moment.  One context
+ *     per host thread.
  */
 #ifndef ALSCORE_H_
 #define ALSCORE_H_
@@ -252,7 +253,7 @@ ALS_API int als_select_smallest(als_ctx* ctx, const float* keys, const int64_t* 
  *   2. ONE ncclAllGather of the records over NVLink (a few hundred KB at most: latency bound);
  *   3. on the device, one launch: the other ranks' score slices complete the local confidence vector, the world*k
  *      candidates are merged with the same block-radix select, unlabelled_confidence is gathered;
- *   4. ONE device->host copy of {ids, unlabelled_confidence}.
+ *   4. the results {ids, unlabelled_confidence} are written by that launch straight into pinned host memory.
  * Every rank returns the same result.  Examples nobody visited keep 0.0 and are selected first, like :685/:701-702.
  */
 
