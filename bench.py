@@ -412,8 +412,18 @@ def main():
             dist.barrier()
         torch.cuda.synchronize()
 
-    for _ in range(max(args.warmup, 3)):
+    # warm-up: at least W (>= 3) untimed steps, and for workloads whose step is a fraction of a millisecond at least 50 ms
+    # of them, so that clocks and caches are where a real pool pass would find them (identical count on every rank)
+    warm_steps = max(args.warmup, 3)
+    t_w = time.perf_counter()
+    for _ in range(warm_steps):
         step(False)
+    torch.cuda.synchronize()
+    per = (time.perf_counter() - t_w) / warm_steps
+    extra = 0 if world > 1 else max(0, min(200, int(0.05 / max(per, 1e-6)) - warm_steps))
+    for _ in range(extra):
+        step(False)
+    warm_steps += extra
     barrier()
     sampler = ClockSampler(local_rank)
     if rank == 0:
@@ -612,7 +622,7 @@ def main():
             desc = sc.describe_launch(dtype, T, chunk, H, W, C, measure)
         line = {
             "metric": "pool pixels scored/s", "value": value, "unit": "Gpix/s", "n_gpus": world,
-            "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": ms_step, "higher_is_better": True,
+            "steps": args.steps, "warmup": warm_steps, "ms_per_step": ms_step, "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": args.dtype, "data": "synthetic",
             "config": {"workload": args.workload + ": " + w["desc"], "pool_images_per_gpu": N, "T": T, "H": H, "W": W,
                        "C": C, "measure": measure, "k": K_SELECT,

@@ -1006,6 +1006,16 @@ int als_rank_pool(als_ctx* ctx, const void* logits, int logits_on_host, int dtyp
   if (k > 0 && !out_ids) return fail(ctx, ALS_ERR_INVALID, "out_ids is NULL");
   DeviceGuard g(ctx->device);
   ALS_TRY(als_pool_begin(ctx, num_examples));  // :684-685
+  // A small `unlabelled` goes up BEFORE the scoring launch (a few microseconds of host work), so that no stream operation
+  // sits between the scoring and the select launch and the latter keeps its programmatic-dependent-launch overlap; a
+  // large one is validated and uploaded while the GPU scores (als_pool_select below).
+  const bool early_upload = M > 0 && M <= 4096;
+  als::SelectBlock blk = als::select_block(k, M);
+  if (early_upload) {
+    ALS_TRY(als::validate_unlabelled(ctx, unlabelled, M));
+    ALS_TRY(als::ensure_select_block(ctx, blk, k));
+    ALS_TRY(als::upload_unlabelled(ctx, unlabelled, M));
+  }
   if (N > 0) {
     std::vector<int64_t> iota;
     const int64_t* idx = example_index;
@@ -1016,8 +1026,20 @@ int als_rank_pool(als_ctx* ctx, const void* logits, int logits_on_host, int dtyp
     }
     ALS_TRY(als_pool_score_batch(ctx, logits, logits_on_host, dtype, T, N, H, W, C, measure, idx));  // :697-700
   }
-  // the GPU is scoring; the host prepares the selection meanwhile
-  return als_pool_select(ctx, unlabelled, M, selection_size, out_ids, out_unlabelled_conf, out_count);  // :705-715
+  if (!early_upload)  // the GPU is scoring; the host prepares the selection meanwhile
+    return als_pool_select(ctx, unlabelled, M, selection_size, out_ids, out_unlabelled_conf, out_count);  // :705-715
+  als::SelectSrc src{};
+  src.mode = 1;
+  src.ids = ctx->sel_ids;
+  src.pool = ctx->pool32;
+  src.lo = INT64_MIN;
+  src.hi = INT64_MAX;
+  const als::SelectOut out = als::select_out_of(ctx, blk, M);
+  int nl = 0;
+  ALS_CUDA(ctx, als::launch_select(src, M, k, als::ScatterDesc{}, als::ExportDesc{}, out, ctx->sel_tmp_keys, ctx->sel_tmp_ids,
+                                   ctx->stream, &nl));  // :705-714
+  ctx->launches += nl;
+  return als::fetch_select_block(ctx, blk, k, M, out_ids, out_unlabelled_conf, out_count);
 }
 
 int als_select_smallest(als_ctx* ctx, const float* keys, const int64_t* ids, int64_t M, int64_t k, float* out_keys,

@@ -470,6 +470,37 @@ def test_rank_confidence_end_to_end(torch, scorer, measure, T):
     assert np.all(u3[np.isin(unl, unseen)] == 0)
 
 
+def test_rank_pool_one_call_equals_three_calls(torch, scorer):
+    """als_rank_pool (:682-715 in one call) == pool_begin + pool_score_batch + pool_select, for device and host logits,
+    shuffled example indices, a pool larger than the batch (unvisited examples stay 0.0), k = 0, an empty and a large
+    unlabelled set (late upload path), and the library's timing hook around the scoring launch."""
+    from oracle import synth
+    N, H, W, C = 12, 16, 24, 19
+    x = synth.synth_logits(1, 0, N, H, W, C)
+    xt = torch.from_numpy(x).cuda()
+    rng = np.random.default_rng(9)
+    for src in (xt, x):
+        for idx, num in ((None, N), (rng.permutation(40)[:N], 40)):
+            unl = np.sort(rng.choice(num, num - 3, replace=False))
+            for k in (5, 0, 100):
+                ids, u = scorer.rank_pool(src, unl, k, "margin", example_index=idx, num_examples=num)
+                scorer.pool_begin(num)
+                scorer.pool_score_batch(src, np.arange(N) if idx is None else idx, "margin")
+                ids2, u2 = scorer.pool_select(unl, k)
+                assert np.array_equal(ids, ids2) and np.array_equal(u, u2), (type(src).__name__, idx is None, k)
+    ids, u = scorer.rank_pool(xt, np.zeros(0, np.int64), 3, "entropy")
+    assert len(ids) == 0 and len(u) == 0
+    big = np.arange(6000)                                            # > 4096 ids: uploaded while the GPU scores
+    ids, u = scorer.rank_pool(xt, big, 7, "entropy", num_examples=6000)
+    assert ids.tolist() == list(range(N, N + 7)) and np.all(u[N:] == 0) and np.all(u[:N] != 0)
+    scorer.enable_timing(True)
+    scorer.rank_pool(xt, np.arange(N), 3, "entropy")
+    assert 0.0 < scorer.last_scoring_ms() < 50.0
+    scorer.enable_timing(False)
+    with pytest.raises(RuntimeError):
+        scorer.last_scoring_ms()
+
+
 def test_dlpack_zero_copy_and_host(torch, scorer):
     from oracle import reference_np as R, synth
     x = synth.synth_logits(1, 0, 3, 8, 16, 19)
