@@ -91,7 +91,7 @@ __global__ void __launch_bounds__(kBlockThreads, Cfg<E, C, true>::MINB) mc_updat
     // front of the shared-memory reads they would hold those back for a global-memory latency
     float x[PPT][CL];
     load_tile_pixels<K, E, C>(stage_base + static_cast<size_t>(s) * K::STAGE_BYTES, pl, class0, nvalid, x);
-    const uint32_t dep = loaded_dep<PPT, CL>(x);
+    const uint32_t dep = loaded_dep<PPT, CL>(x) | (static_cast<uint32_t>(npix) >> 1);  // npix: same stage, read late
     __syncwarp();
     if (lane == 0) mbar_arrive_after_loads(&empty[s], dep);
     if (++s == nstage) { s = 0; ph ^= 1u; }

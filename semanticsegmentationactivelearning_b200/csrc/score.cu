@@ -143,7 +143,8 @@ __global__ void __launch_bounds__(kBlockThreads, Cfg<E, C, (MEASURE == kMulti)>:
       // Pixel slots past the end of the pool (last tile only) hold stale but in-bounds bytes:
       // they are computed like the rest (no divergence around the shuffles) and dropped at emit.
       load_tile_pixels<K, E, C>(stage_base + static_cast<size_t>(s) * K::STAGE_BYTES, pl, class0, nvalid, x);
-      const uint32_t dep = loaded_dep<PPT, CL>(x);
+      // (the tile descriptor sits in the same stage: the fields only the rare emit path reads join the dependency)
+      const uint32_t dep = loaded_dep<PPT, CL>(x) | (static_cast<uint32_t>(off) >> 1) | (static_cast<uint32_t>(npix) >> 1);
       __syncwarp();
       if (lane == 0) mbar_arrive_after_loads(&empty[s], dep);  // values are in registers: hand the stage back
       if (++s == nstage) { s = 0; ph ^= 1u; }
@@ -202,7 +203,7 @@ __global__ void __launch_bounds__(kBlockThreads, Cfg<E, C, (MEASURE == kMulti)>:
         float x[PPT][CL];
         if (t > 0) mbar_wait(&full[s], ph);
         load_tile_pixels<K, E, C>(stage_base + static_cast<size_t>(s) * K::STAGE_BYTES, pl, class0, nvalid, x);
-        const uint32_t dep = loaded_dep<PPT, CL>(x);
+        const uint32_t dep = loaded_dep<PPT, CL>(x) | (static_cast<uint32_t>(off) >> 1) | (static_cast<uint32_t>(npix) >> 1);
         __syncwarp();
         if (lane == 0) mbar_arrive_after_loads(&empty[s], dep);
         if (++s == nstage) { s = 0; ph ^= 1u; }
