@@ -301,6 +301,21 @@ struct ImageAcc {
     nan |= (conf != conf) ? 1u : 0u;
     sum += static_cast<int>(__float_as_uint(conf + 3.0f) - 0x40400000u);
   }
+  // the same for the N pixels of a thread at once: the raw mantissa words are summed in 32 bits (each is below 2^23 in
+  // magnitude once the bias is taken off, N <= 4) and widened once
+  template <int N>
+  __device__ __forceinline__ void add_q22(const float (&conf)[N]) {
+    static_assert(N <= 64, "32-bit partial sum");
+    unsigned int q = 0;
+    bool bad = false;
+#pragma unroll
+    for (int k = 0; k < N; ++k) {
+      q += __float_as_uint(conf[k] + 3.0f);
+      bad |= conf[k] != conf[k];
+    }
+    nan |= bad ? 1u : 0u;
+    sum += static_cast<int>(q - static_cast<unsigned int>(N) * 0x40400000u);
+  }
 
   __device__ __forceinline__ void flush(const ScoreParams& p) {  // warp-collective
     const long long s = warp_sum_ll(sum);

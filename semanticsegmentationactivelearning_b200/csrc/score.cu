@@ -163,10 +163,11 @@ __global__ void __launch_bounds__(kBlockThreads, Cfg<E, C, (MEASURE == kMulti)>:
       }
       if (plain) {
         if (sub == 0) {
+          if constexpr (ES == 2) {
+            acc.add_q22(conf);  // bf16: XU-bound kernel, conversion moved off the XU pipe
+          } else {
 #pragma unroll
-          for (int k = 0; k < PPT; ++k) {
-            if constexpr (ES == 2) acc.add_q22(conf[k]);  // bf16: XU-bound kernel, conversion moved off the XU pipe
-            else acc.add(conf[k], p.fx_scale);
+            for (int k = 0; k < PPT; ++k) acc.add(conf[k], p.fx_scale);
           }
         }
       } else if (in_img == K::TILE_PIX) {  // per-pixel outputs, full tile inside one image
