@@ -13,6 +13,7 @@
 #include <string.h>
 
 #include <mutex>
+#include <string>
 #include <vector>
 
 #include "ctx.h"
