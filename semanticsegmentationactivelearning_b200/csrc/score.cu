@@ -443,9 +443,27 @@ LaunchPlan plan_score(int dtype, int C, int measure, int T, long long total_pixe
   return plan;
 }
 
+int max_claim(int T, int dtype) {
+  static const int env = [] {
+    const char* e = getenv("ALS_CLAIM");  // bring-up knob
+    return e ? atoi(e) : 0;
+  }();
+  if (T != 1) return 1;
+  if (env > 0) return env;
+  return dtype == 0 ? 2 : 16;
+}
+
+int claim_shift_for(int grid) {
+  int s = 2;
+  while ((1ll << s) < 4ll * grid) ++s;
+  return s;
+}
+
 cudaError_t launch_score(const LaunchPlan& plan, int dtype, ScoreParams p, cudaStream_t stream) {
   if (p.total_pixels <= 0) return cudaSuccess;
   p.any_out = (p.conf_map || p.label || p.mask) ? 1 : 0;
+  p.claim = max_claim(p.T, dtype);
+  p.claim_shift = claim_shift_for(plan.grid);
   cudaError_t err;
   if (plan.tiled) {
     p.stages = plan.stages;
