@@ -6,10 +6,11 @@ sys.path.insert(0, ".")
 from semanticsegmentationactivelearning_b200 import Scorer
 sc = Scorer(0)
 shape = (2, 512, 1024, 19)
-k = 3
+k = int(sys.argv[1]) if len(sys.argv) > 1 else 3
+reps = int(sys.argv[2]) if len(sys.argv) > 2 else 40
 x8 = sc.synth_logits(8, 3, *shape)
 ref = sc.pseudo_annotation(x8[:k].contiguous(), "confidence")["pseudo_confidence"].clone()
-for rep in range(40):
+for rep in range(reps):
     sc.mc_begin(shape)
     for t in range(k):
         sc.mc_add_sample(x8[t])

@@ -51,21 +51,28 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
   }
 }
 
-// Release of a TMA-filled shared-memory stage by a warp that has READ it with ordinary ld.shared: the arrive must not be
-// performed before those loads have actually read shared memory, or the producer's next bulk copy can overwrite bytes
-// that are still to be read (write-after-read across the generic and the async proxy).  Nothing in the instruction
-// stream orders them by itself: LDS results are tracked by the scoreboard, SYNCS.ARRIVE reads no loaded register, so it
-// can be issued -- and performed -- while the loads sit in the memory pipeline.  Seen for real in mc.cu (state LDGs
-// queued in front of the LDS: a handful of pixels of one tile per ~10 launches read the NEXT tile's logits).  The cure is
-// a true register dependency: `dep` is derived from every loaded register (callers pass bits >> 1, so it is never
-// 0xffffffff) and predicates the arrive, which therefore waits for the loads' scoreboard.
-__device__ __forceinline__ void mbar_arrive_after_loads(uint64_t* bar, uint32_t dep) {
+// Stage release that cannot overtake the loads of the stage (WAR on a TMA-filled buffer).  `mbarrier.arrive` does not
+// wait for the arriving thread's in-flight ld.shared: the producer may see the slot free and the bulk copy may overwrite
+// bytes that have not been read yet.  The arrival is therefore made DATA dependent on the loaded registers: it is
+// predicated on `dep != never`, where `dep` is a word computed from every loaded value and `never` is a launch parameter
+// (always 0xffffffff; `dep` has its top bit clear, so the test is always true) -- a RUN-TIME value on purpose: against a
+// literal, ptxas proves the test from the shift that clears the top bit, folds it and drops the dependency (round 2
+// shipped that for a while: the arrival then sits wherever the scheduler puts it, usually late enough, and a single
+// class value of a single pixel was read stale about once in 300 streamed runs, profiles/r02_mc_single_pixel.txt).
+__device__ __forceinline__ void mbar_arrive_after_loads(uint64_t* bar, uint32_t dep, uint32_t never) {
   asm volatile(
       "{\n\t.reg .pred p;\n\t"
-      "setp.ne.u32 p, %1, 0xffffffff;\n\t"
+      "setp.ne.u32 p, %1, %2;\n\t"
       "@p mbarrier.arrive.shared::cta.b64 _, [%0];\n\t}"
-      ::"r"(smem_u32(bar)), "r"(dep)
+      ::"r"(smem_u32(bar)), "r"(dep), "r"(never)
       : "memory");
+}
+
+// Warp-level form: ONE arrival per warp, issued by lane 0, that waits for the loads of EVERY lane -- the OR-reduction
+// (REDUX) needs each lane's word, so it holds the arrival back for all of them however the lanes were scheduled.
+__device__ __forceinline__ void warp_release_after_loads(uint64_t* bar, uint32_t dep, int lane, uint32_t never) {
+  const uint32_t all = __reduce_or_sync(0xffffffffu, dep);
+  if (lane == 0) mbar_arrive_after_loads(bar, all, never);
 }
 
 // For waits that are expected to be long: back off between polls so that the spinning warp does not take

@@ -483,8 +483,7 @@ score_head_kernel(const HeadParams p, const __grid_constant__ CUtensorMap feat_m
         uint32_t dep = 0;
 #pragma unroll
         for (int c = 0; c < 4; ++c) dep |= __float_as_uint(own[c].x) | __float_as_uint(left[c].x);
-        __syncwarp();
-        if (lane == 0) mbar_arrive_after_loads(&empty_raw[s_row], dep >> 1);
+        warp_release_after_loads(&empty_raw[s_row], dep >> 1, lane, p.sp.never);
         // split in registers while the tensor-memory slot may still be in use, then only the stores wait for it
         uint32_t hi_o[16], lo_o[16], hi_l[16], lo_l[16];
         split_hi_lo(own, hi_o, lo_o);
@@ -863,6 +862,7 @@ static cudaError_t make_feature_map(const HeadParams& p, CUtensorMap* map) {
 cudaError_t launch_head(const HeadPlan& plan, HeadParams p, cudaStream_t stream) {
   if (p.n_units <= 0) return cudaSuccess;
   p.sp.any_out = (p.sp.conf_map || p.sp.label || p.sp.mask) ? 1 : 0;
+  p.sp.never = 0xffffffffu;
   cudaError_t err = cudaFuncSetAttribute(plan.func, cudaFuncAttributeMaxDynamicSharedMemorySize, plan.smem_bytes);
   if (err != cudaSuccess) return err;
   const long long grid = p.n_units < plan.grid ? p.n_units : plan.grid;

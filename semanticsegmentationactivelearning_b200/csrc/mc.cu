@@ -92,8 +92,7 @@ __global__ void __launch_bounds__(kBlockThreads, Cfg<E, C, true>::MINB) mc_updat
     float x[PPT][CL];
     load_tile_pixels<K, E, C>(stage_base + static_cast<size_t>(s) * K::STAGE_BYTES, pl, class0, nvalid, x);
     const uint32_t dep = loaded_dep<PPT, CL>(x) | (static_cast<uint32_t>(npix) >> 1);  // npix: same stage, read late
-    __syncwarp();
-    if (lane == 0) mbar_arrive_after_loads(&empty[s], dep);
+    warp_release_after_loads(&empty[s], dep, lane, p.never);
     if (++s == nstage) { s = 0; ph ^= 1u; }
 
     float nmu[PPT][CL];
@@ -340,6 +339,7 @@ cudaError_t launch_mc_update(const McPlan& plan, int dtype, ScoreParams p, float
   p.T = 1;
   p.sample_stride = 0;
   p.any_out = 0;
+  p.never = 0xffffffffu;
   p.claim_shift = claim_shift_for(plan.grid);
   p.claim = 1;  // runs of tiles were measured on the streamed update too: 1.016 -> 1.007 (2) -> 0.996 (4) of the copy peak
   if (plan.tiled) {

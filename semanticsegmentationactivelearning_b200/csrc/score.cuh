@@ -18,8 +18,9 @@ struct ScoreParams {
   int measure;
   int stages;
   int any_out;  // conf_map || label || mask (set by launch_score)
+  unsigned int never;  // 0xffffffff: the value a stage-release dependency word never takes (common.cuh; set by the launchers)
   int claim;    // most tiles a producer takes from the dynamic scheduler per atomic (set by the launchers; >= 1)
-  int claim_shift;  // ceil(log2(4 * grid)): runs shrink once fewer than claim << claim_shift tiles are left (launchers)
+  int claim_shift;  // ceil(log2(2 * grid)): runs shrink once fewer than claim << claim_shift tiles are left (launchers)
   float inv_log2_c;  // 1 / log2(C): entropy in bits -> H / log(float32(C))   (active_learning.py:248-249)
   float threshold;  // alparams["threshold"]      (active_learning.py:265)
   float inv_T;
@@ -50,7 +51,7 @@ constexpr int kFusedFinalizeMaxImages = 2048;
 // Longest run of consecutive tiles a CTA takes from the scheduler at once (produce_tiles, tiles.cuh).  A T > 1 tile
 // is T stages already: 1.  T = 1, one ~20 KB stage per tile: f32 2 (reaches the same DRAM rate as T = 8 launches;
 // longer runs only lengthen the tail of a batch-of-8 call), bf16 16 (XU- and issue-bound: the producer thread's
-// per-tile instruction chain is what runs amortise; measured 0.865 -> 0.979 (8) -> 0.985 (16) of the copy peak on cfg3).
+// per-tile instruction chain is what runs amortise; cfg3 went 0.865 -> 0.93 of the copy peak with runs of 16).
 int max_claim(int T, int dtype);
 int claim_shift_for(int grid);
 

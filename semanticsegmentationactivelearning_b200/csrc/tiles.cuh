@@ -182,7 +182,7 @@ __device__ __forceinline__ void load_tile_pixels(const unsigned char* __restrict
 
 // A word that depends on every register load_tile_pixels() filled (see mbar_arrive_after_loads): the per-pixel class
 // maximum -- the first thing every measure computes anyway, so the chain is shared with it -- OR-ed over the thread's
-// pixels, shifted right so that it can never be all ones.
+// pixels, shifted right so that it can never be all ones (= ScoreParams::never, see warp_release_after_loads).
 template <int PPT, int CL>
 __device__ __forceinline__ uint32_t loaded_dep(const float (&x)[PPT][CL]) {
   uint32_t d = 0;
@@ -238,10 +238,10 @@ __device__ __forceinline__ void produce_tiles(const ScoreParams& p, uint64_t* fu
     // Guided self-scheduling.  At the FIRST tile of a run the run after it is claimed, so the atomic's round trip
     // (~1 us under load, about the time a CTA has per 20 KB tile at 7.5 TB/s) hides behind the whole run; one atomic
     // per tile, consumed one tile later, held T = 1 launches ~5 % (f32) to ~8 % (bf16) under what they reach with
-    // runs.  Runs are up to p.claim tiles while there is plenty left (more than four runs per CTA) and shrink to single
+    // runs.  Runs are up to p.claim tiles while there is plenty left (more than two runs per CTA) and shrink to single
     // tiles towards the end, so the tail stays short.
     if (live && !claimed) {
-      long long n = (p.num_tiles - run_end) >> p.claim_shift;  // tiles left / (4 * grid, rounded up to a power of two)
+      long long n = (p.num_tiles - run_end) >> p.claim_shift;  // tiles left / (2 * grid, rounded up to a power of two)
       n = n < 1 ? 1 : (n > p.claim ? p.claim : n);
       next = static_cast<long long>(gridDim.x) +
              static_cast<long long>(atomicAdd(p.tile_counter, static_cast<unsigned long long>(n)));
